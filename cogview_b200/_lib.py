@@ -1,0 +1,70 @@
+"""ctypes binding of libcogview_b200.so (the C ABI declared in include/cogview_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcogview_b200.so")
+
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_int64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+
+class CogViewB200Error(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    lib.cv_version.restype = c_int
+    lib.cv_last_error.restype = ctypes.c_char_p
+    sigs = {
+        "cv_gemm_bf16": [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p,
+                         c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    return sigs
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CogViewB200Error(
+                "libcogview_b200.so not found at %s — build it with `python -m cogview_b200.csrc.build` "
+                "(there is no fallback path)" % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc, name="call"):
+    if rc != 0:
+        msg = lib().cv_last_error()
+        raise CogViewB200Error("%s failed (rc=%d): %s" % (name, rc, msg.decode() if msg else "?"))
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise CogViewB200Error("cogview_b200 kernels need CUDA tensors; got a %s tensor (no CPU fallback)"
+                                   % t.device)

@@ -1,0 +1,352 @@
+// cv_gemm_bf16: C[M,N] = op(A)[M,K] * op(B)[N,K]^T (+ bias) (+ tanh-GELU), bf16 operands, fp32 accumulate.
+//
+// Replaces the cuBLAS GEMMs the reference reaches through F.linear:
+//   ColumnParallelLinear.forward  /root/reference/mpu/layers.py:239-249   (QKV, h->4h: bias fused)
+//   RowParallelLinear.forward     /root/reference/mpu/layers.py:312-326   (out-proj, 4h->h: bias fused)
+//   gelu_impl                     /root/reference/mpu/sparse_transformer.py:172-176 (fused epilogue)
+//   logits GEMM                   /root/reference/model/gpt2_modeling.py:117-118
+// and their autograd backward (dgrad: B MN-major; wgrad: A and B MN-major).
+//
+// Design (sm_100a): persistent, one CTA per SM, 6 warps.
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles -> 128B-swizzled smem ring (4-6 stages)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM;
+//               two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps tile i+1
+//   warps 2-5   epilogue: tcgen05.ld -> bias/GELU/abs-max -> swizzled smem staging -> TMA store
+#include "common.cuh"
+#include "host.h"
+#include "../../include/cogview_b200.h"
+
+namespace {
+
+using namespace cv;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_BYTES = 128 * 128;  // 128 rows x 128 bytes
+
+template <int BN>
+struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+    int M, N, K;
+    int num_m_blocks, num_n_blocks, num_k_blocks;
+    const __nv_bfloat16* bias;  // [N] or null
+    int act;                    // 0 none, 1 tanh-GELU
+    float* absmax;              // null or scalar: atomicMax |C| over valid entries
+    int has_c2;                 // second bf16 output = pre-activation (bias added, no GELU)
+};
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* epi_buf = smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + 2 * EPI_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]
+    uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
+    uint64_t* tmem_full = bars + 2 * C::STAGES;      // [2]
+    uint64_t* tmem_empty = bars + 2 * C::STAGES + 2; // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 1) tmem_alloc<2 * BN>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp_idx == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile % p.num_m_blocks) * BM;
+                const int n0 = (tile / p.num_m_blocks) * BN;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * C::STAGE_BYTES;
+                    uint8_t* sB = sA + C::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_2d(sA + i * (BK * 128), &tmA, &full_bar[stage], m0 + i * 64, kb * BK);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_2d(sB + i * (BK * 128), &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            // K-major: 8-row groups 1024 B apart. MN-major: 64-element chunks one TMA box (BK*128 B) apart,
+            // 8-row K groups 1024 B apart.
+            constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0, B_LBO = B_MN ? BK * 128 : 0;
+            constexpr uint32_t A_KSTEP = A_MN ? 16 * 128 : 32, B_KSTEP = B_MN ? 16 * 128 : 32;
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(a_addr + k * A_KSTEP, A_LBO, 1024);
+                        const uint64_t db = make_smem_desc_sw128(b_addr + k * B_KSTEP, B_LBO, 1024);
+                        umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[as]);  // accumulator complete
+            }
+        }
+    } else {
+        // ------------------------------ epilogue warps ------------------------------
+        const int q = warp_idx & 3;             // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;          // row within the tile
+        const int epi_tid = threadIdx.x - 64;   // 0..127
+        constexpr int EPI_COLS = OUT_F32 ? 32 : 64;
+        constexpr int NCHUNK = BN / EPI_COLS;
+        int it = 0;
+        uint32_t buf_sel = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile % p.num_m_blocks) * BM;
+            const int n0 = (tile / p.num_m_blocks) * BN;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const bool row_ok = (m0 + row) < p.M;
+            float tmax = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; ++c) {
+                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * EPI_COLS;
+                uint32_t r[EPI_COLS];
+                {
+                    uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+                    tmem_ld_x32(taddr, r0);
+                    if (EPI_COLS == 64) {
+                        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[EPI_COLS - 32]);
+                        tmem_ld_x32(taddr + 32, r1);
+                    }
+                }
+                tmem_ld_wait();
+                if (c == NCHUNK - 1) {
+                    // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[as]);
+                }
+                const int ncol0 = n0 + c * EPI_COLS;
+                float v[EPI_COLS];
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) {
+                    float x = __uint_as_float(r[j]);
+                    if (p.bias != nullptr) {
+                        const int n = ncol0 + j;
+                        x += (n < p.N) ? __bfloat162float(p.bias[n]) : 0.f;
+                    }
+                    v[j] = x;
+                }
+                const int rounds = p.has_c2 ? 2 : 1;
+                for (int round = 0; round < rounds; ++round) {
+                    const bool is_pre = p.has_c2 && round == 0;
+                    if (!is_pre && p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < EPI_COLS; ++j) v[j] = gelu_tanh(v[j]);
+                    }
+                    uint8_t* buf = epi_buf + (buf_sel & 1) * EPI_BYTES;
+                    if (epi_tid == 0) tma_store_wait_read<1>();  // the store that last read `buf` has drained
+                    named_bar_sync(1, 128);
+                    uint8_t* rowp = buf + row * 128;
+                    if (OUT_F32) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            *reinterpret_cast<float4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+                        }
+                        if (!is_pre && p.absmax != nullptr && row_ok) {
+#pragma unroll
+                            for (int j = 0; j < EPI_COLS; ++j)
+                                if (ncol0 + j < p.N) tmax = fmaxf(tmax, fabsf(v[j]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            uint4 o;
+                            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+                        }
+                        if (!is_pre && p.absmax != nullptr && row_ok) {
+#pragma unroll
+                            for (int j = 0; j < EPI_COLS; ++j)
+                                if (ncol0 + j < p.N) tmax = fmaxf(tmax, fabsf(bf16_round(v[j])));
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (epi_tid == 0) {
+                        tma_store_2d(is_pre ? &tmC2 : &tmC, buf, ncol0, m0);
+                        tma_store_commit();
+                    }
+                    ++buf_sel;
+                }
+            }
+            if (p.absmax != nullptr) {
+                tmax = warp_max(tmax);
+                if (lane == 0 && tmax > 0.f) atomic_max_nonneg(p.absmax, tmax);
+            }
+        }
+        if (epi_tid == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+           const GemmParams& p, cudaStream_t stream) {
+    auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) return cvh::fail_cuda("cv_gemm_bf16", e);
+        attr_set = true;
+    }
+    int tiles = p.num_m_blocks * p.num_n_blocks;
+    int grid = tiles < cvh::num_sms() ? tiles : cvh::num_sms();
+    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cvh::fail_cuda("cv_gemm_bf16", e);
+    return 0;
+}
+
+template <int BN>
+int dispatch(int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+             const CUtensorMap& tmC2, const GemmParams& p, cudaStream_t s) {
+    if (out_f32) {
+        if (!a_mn && !b_mn) return launch<BN, false, false, true>(tmA, tmB, tmC, tmC2, p, s);
+        if (!a_mn && b_mn) return launch<BN, false, true, true>(tmA, tmB, tmC, tmC2, p, s);
+        if (a_mn && b_mn) return launch<BN, true, true, true>(tmA, tmB, tmC, tmC2, p, s);
+        return cvh::fail_arg("cv_gemm_bf16", "A MN-major with B K-major is not instantiated");
+    }
+    if (!a_mn && !b_mn) return launch<BN, false, false, false>(tmA, tmB, tmC, tmC2, p, s);
+    if (!a_mn && b_mn) return launch<BN, false, true, false>(tmA, tmB, tmC, tmC2, p, s);
+    if (a_mn && b_mn) return launch<BN, true, true, false>(tmA, tmB, tmC, tmC2, p, s);
+    return cvh::fail_arg("cv_gemm_bf16", "A MN-major with B K-major is not instantiated");
+}
+
+}  // namespace
+
+extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                            void* Cout, int c_is_f32, int64_t ldc, void* C2, const void* bias, int act, float* absmax,
+                            int M, int N, int K, int block_n, void* stream) {
+    CV_REQUIRE(A && B && Cout, "null operand");
+    CV_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
+    CV_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
+    CV_REQUIRE(c_is_f32 ? (ldc % 4 == 0) : (ldc % 8 == 0), "ldc must give 16-byte aligned rows");
+    CV_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(Cout) & 15) == 0,
+               "operands must be 16-byte aligned");
+    CV_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (tanh-GELU)");
+    CV_REQUIRE(!(C2 && c_is_f32), "pre-activation output requires bf16 C");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    int BN = block_n;
+    if (BN == 0) {
+        // fewest (waves x tile width) on the SM count; ties go to the wider tile
+        const int sms = cvh::num_sms();
+        const int mb = (M + BM - 1) / BM;
+        auto cost = [&](int bn) {
+            long tiles = (long)mb * ((N + bn - 1) / bn);
+            return ((tiles + sms - 1) / sms) * bn;
+        };
+        BN = (cost(128) < cost(256)) ? 128 : 256;
+    }
+    CV_REQUIRE(BN == 128 || BN == 256, "block_n must be 0 (auto), 128 or 256");
+
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.num_m_blocks = (M + BM - 1) / BM;
+    p.num_n_blocks = (N + BN - 1) / BN;
+    p.num_k_blocks = (K + BK - 1) / BK;
+    p.bias = static_cast<const __nv_bfloat16*>(bias);
+    p.act = act;
+    p.absmax = absmax;
+    p.has_c2 = C2 != nullptr;
+
+    alignas(64) CUtensorMap tmA, tmB, tmC, tmC2;
+    int rc;
+    // K-major: stored [rows = M or N, cols = K], box [tile rows x 64]. MN-major: stored [K, M or N], box [64 x 64].
+    rc = a_mn_major ? cvh::encode_tmap_2d_bf16(&tmA, A, K, M, lda, BK, 64)
+                    : cvh::encode_tmap_2d_bf16(&tmA, A, M, K, lda, BM, BK);
+    if (rc) return rc;
+    rc = b_mn_major ? cvh::encode_tmap_2d_bf16(&tmB, B, K, N, ldb, BK, 64)
+                    : cvh::encode_tmap_2d_bf16(&tmB, B, N, K, ldb, BN, BK);
+    if (rc) return rc;
+    rc = c_is_f32 ? cvh::encode_tmap_2d_f32(&tmC, Cout, M, N, ldc, BM, 32)
+                  : cvh::encode_tmap_2d_bf16(&tmC, Cout, M, N, ldc, BM, 64);
+    if (rc) return rc;
+    if (C2) {
+        rc = cvh::encode_tmap_2d_bf16(&tmC2, C2, M, N, ldc, BM, 64);
+        if (rc) return rc;
+    } else {
+        tmC2 = tmC;
+    }
+    if (BN == 256) return dispatch<256>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, tmC, tmC2, p, s);
+    return dispatch<128>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, tmC, tmC2, p, s);
+}

@@ -1,0 +1,50 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, TMA tensor-map
+// encoding through the driver entry point (no link-time dependency on libcuda), launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace cvh {
+
+// last-error string returned by cv_last_error() (thread-local: entry points are re-entrant)
+std::string& last_error();
+int fail_arg(const char* fn, const char* msg);          // returns a negative code (argument error)
+int fail_cuda(const char* fn, cudaError_t e);           // returns the positive cudaError_t
+int fail_cu(const char* fn, CUresult r);                // driver error while encoding a tensor map
+
+#define CV_REQUIRE(cond, msg)                                  \
+    do {                                                       \
+        if (!(cond)) return cvh::fail_arg(__func__, msg);      \
+    } while (0)
+
+#define CV_CUDA(expr)                                          \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return cvh::fail_cuda(__func__, _e); \
+    } while (0)
+
+#define CV_LAUNCH_CHECK()                                      \
+    do {                                                       \
+        cudaError_t _e = cudaGetLastError();                   \
+        if (_e != cudaSuccess) return cvh::fail_cuda(__func__, _e); \
+    } while (0)
+
+int num_sms();
+
+enum class Swizzle { None, B128 };
+
+// Encode a tiled tensor map.  dims/strides are innermost-first, strides in BYTES for dims 1..rank-1.
+// elem_strides may be null (all ones).  Returns 0 or an error code (with last_error set).
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, Swizzle swz);
+
+// 2-D row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols]
+int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_rows, uint32_t box_cols);
+int encode_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                       uint32_t box_rows, uint32_t box_cols);
+
+}  // namespace cvh

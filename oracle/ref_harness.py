@@ -1,0 +1,95 @@
+"""TEST INFRASTRUCTURE — imports the UNMODIFIED reference modules from /root/reference on CPU.
+
+Only usable in the build container (the GPU box has no /root/reference).  Used by
+oracle/make_golden.py to (a) validate the travelling restatement oracle/cogview_oracle.py against the
+real reference and (b) generate the golden fixtures under tests/golden/.
+
+Harness-side shims (no edits to the reference):
+  1. fake `apex`:  FusedLayerNorm = torch.nn.LayerNorm, FusedAdam = torch.optim.AdamW
+     (imports at mpu/sparse_transformer.py:23, mpu/layers.py:28)
+  2. fake `deepspeed` with checkpointing.is_configured() -> False (mpu/sparse_transformer.py:30,107,465)
+  3. sys.modules['torch._six'] with `inf` (mpu/grads.py:22; removed in torch >= 2)
+  4. on CPU, mpu.sparse_transformer.get_cuda_rng_tracker -> no-op fork(), because standard_attention
+     forks the CUDA RNG unconditionally (mpu/sparse_transformer.py:667-669)
+plus torch.distributed gloo world_size=1 and mpu.initialize_model_parallel(1).
+"""
+import contextlib
+import os
+import sys
+import types
+
+import torch
+
+REFERENCE_ROOT = os.environ.get("COGVIEW_REFERENCE", "/root/reference")
+
+_loaded = {}
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mpu"))
+
+
+def _install_shims():
+    apex = types.ModuleType("apex")
+    norm = types.ModuleType("apex.normalization")
+    fln = types.ModuleType("apex.normalization.fused_layer_norm")
+    fln.FusedLayerNorm = torch.nn.LayerNorm
+    norm.fused_layer_norm = fln
+    apex.normalization = norm
+    opt = types.ModuleType("apex.optimizers")
+    opt.FusedAdam = torch.optim.AdamW
+    apex.optimizers = opt
+    sys.modules.setdefault("apex", apex)
+    sys.modules.setdefault("apex.normalization", norm)
+    sys.modules.setdefault("apex.normalization.fused_layer_norm", fln)
+    sys.modules.setdefault("apex.optimizers", opt)
+
+    ds = types.ModuleType("deepspeed")
+    ck = types.ModuleType("deepspeed.checkpointing")
+    ck.is_configured = lambda: False
+    ds.checkpointing = ck
+    ds.add_config_arguments = lambda parser: parser
+    sys.modules.setdefault("deepspeed", ds)
+    sys.modules.setdefault("deepspeed.checkpointing", ck)
+
+    six = types.ModuleType("torch._six")
+    six.inf = float("inf")
+    sys.modules.setdefault("torch._six", six)
+
+
+class _NoRng:
+    @contextlib.contextmanager
+    def fork(self, *a, **k):
+        yield
+
+
+def load():
+    """Returns a dict with the reference's `mpu`, `gpt2_modeling` (model) and `vqvae` modules."""
+    if _loaded:
+        return _loaded
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    _install_shims()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    import mpu  # noqa: the reference's package
+    import mpu.sparse_transformer as st
+    if not torch.cuda.is_available():
+        st.get_cuda_rng_tracker = lambda: _NoRng()
+    mpu.initialize_model_parallel(1)
+    from model import gpt2_modeling
+    import vqvae.api as vq_api
+    import vqvae.vqvae_zc as vq_zc
+    _loaded.update(mpu=mpu, sparse_transformer=st, gpt2_modeling=gpt2_modeling, vq_api=vq_api, vq_zc=vq_zc)
+    return _loaded
+
+
+def unload_paths():
+    """Remove the reference from sys.path / sys.modules so the repo's own `mpu`-mirror can be imported."""
+    if REFERENCE_ROOT in sys.path:
+        sys.path.remove(REFERENCE_ROOT)
