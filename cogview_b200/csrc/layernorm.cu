@@ -1,0 +1,250 @@
+// Abs-max pre-scaled LayerNorm (the reference's `LayerNorm`, /root/reference/mpu/sparse_transformer.py:40-44):
+//     y = FusedLayerNorm(x / (max|x| / 8)),   max over the WHOLE tensor, detached
+// which is algebraically LN with a data-dependent epsilon:  (x - mu) / sqrt(var + eps * c^2) * gamma + beta,
+// c = max|x| / 8.  The scalar max|x| is produced by whichever kernel wrote x (GEMM epilogue, the
+// residual-adding variant of this kernel, or the embedding kernel) via atomicMax, so no extra pass over x.
+//
+// Sandwich-LN fusion (mpu/sparse_transformer.py:314-342): the `third`/`fourth` LayerNorms are applied to a
+// bf16 GEMM output and immediately added to the fp32 residual stream; that variant (RES) also emits
+// max|residual_out| for the LayerNorm that follows.
+//
+// HBM-bound: one warp per row, the row is staged once in shared memory (fp32) and re-read from there.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/cogview_b200.h"
+
+namespace {
+using namespace cv;
+
+constexpr int WARPS = 8;
+
+__device__ __forceinline__ float ld_as_float(const float* p, int i) { return p[i]; }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p, int i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void st_from_float(float* p, int i, float v) { p[i] = v; }
+__device__ __forceinline__ void st_from_float(__nv_bfloat16* p, int i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// vector loads of 4 consecutive elements
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float round_as(float v, const float*) { return v; }
+__device__ __forceinline__ float round_as(float v, const __nv_bfloat16*) { return bf16_round(v); }
+
+template <typename TIn, typename TOut, bool RES>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ absmax_in, const __nv_bfloat16* __restrict__ gamma,
+              const __nv_bfloat16* __restrict__ beta, float eps, const float* __restrict__ residual,
+              TOut* __restrict__ out, float* __restrict__ absmax_out, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, int rows, int cols) {
+    extern __shared__ float srow_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* srow = srow_all + warp * cols;
+    const float c = *absmax_in * 0.125f;
+    const float eps_eff = eps * c * c;
+    const float inv_n = 1.0f / cols;
+    float omax = 0.f;
+    for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
+        const TIn* xr = x + (size_t)row * cols;
+        float s = 0.f;
+        for (int i = lane * 4; i < cols; i += 128) {
+            float4 v = ld4(xr + i);
+            st4(srow + i, v);
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+        const float mean = warp_sum(s) * inv_n;
+        float ss = 0.f;
+        for (int i = lane * 4; i < cols; i += 128) {
+            float4 v = ld4(srow + i);
+            float a = v.x - mean, b = v.y - mean, d = v.z - mean, e = v.w - mean;
+            ss += (a * a + b * b) + (d * d + e * e);
+        }
+        const float var = warp_sum(ss) * inv_n;
+        const float rstd = rsqrtf(var + eps_eff);
+        if (lane == 0 && mean_out != nullptr) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+        TOut* orow = out + (size_t)row * cols;
+        for (int i = lane * 4; i < cols; i += 128) {
+            float4 v = ld4(srow + i);
+            float4 g = ld4(gamma + i), bt = ld4(beta + i);
+            float4 y;
+            y.x = (v.x - mean) * rstd * g.x + bt.x;
+            y.y = (v.y - mean) * rstd * g.y + bt.y;
+            y.z = (v.z - mean) * rstd * g.z + bt.z;
+            y.w = (v.w - mean) * rstd * g.w + bt.w;
+            if (RES) {
+                float4 r = ld4(residual + (size_t)row * cols + i);
+                y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+            }
+            st4(orow + i, y);
+            if (absmax_out != nullptr) {
+                omax = fmaxf(omax, fmaxf(fmaxf(fabsf(round_as(y.x, orow)), fabsf(round_as(y.y, orow))),
+                                         fmaxf(fabsf(round_as(y.z, orow)), fabsf(round_as(y.w, orow)))));
+            }
+        }
+        __syncwarp();
+    }
+    if (absmax_out != nullptr) {
+        omax = warp_max(omax);
+        if (lane == 0 && omax > 0.f) atomic_max_nonneg(absmax_out, omax);
+    }
+}
+
+// Backward.  dy: gradient of the LN output (TDy); dres (optional fp32): gradient already flowing on the
+// residual path that must be added to dx (fp32 output) — used for the input/post-attention/final LNs.
+//   dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)),  xhat = (x - mean) * rstd
+// dgamma/dbeta partial sums per CTA go to `partials` [gridDim.x, 2, cols]; ln_bwd_finalize reduces them.
+template <typename TIn, typename TDy, typename TDx>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_bwd_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const float* __restrict__ mean_in,
+              const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ gamma,
+              const float* __restrict__ dres, TDx* __restrict__ dx, float* __restrict__ partials, int rows,
+              int cols) {
+    extern __shared__ float smem_f[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sx = smem_f + (size_t)warp * 2 * cols;   // xhat
+    float* sg = sx + cols;                            // dy (raw)
+    float* sdg = smem_f + (size_t)WARPS * 2 * cols;   // [cols] dgamma accum (block-shared)
+    float* sdb = sdg + cols;
+    for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) sdg[i] = 0.f;
+    __syncthreads();
+    const float inv_n = 1.0f / cols;
+    for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        const TIn* xr = x + (size_t)row * cols;
+        const TDy* dyr = dy + (size_t)row * cols;
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = lane * 4; i < cols; i += 128) {
+            float4 v = ld4(xr + i), d = ld4(dyr + i), g = ld4(gamma + i);
+            float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+            st4(sx + i, xh);
+            st4(sg + i, d);
+            float a0 = g.x * d.x, a1 = g.y * d.y, a2 = g.z * d.z, a3 = g.w * d.w;
+            s1 += (a0 + a1) + (a2 + a3);
+            s2 += (a0 * xh.x + a1 * xh.y) + (a2 * xh.z + a3 * xh.w);
+        }
+        s1 = warp_sum(s1) * inv_n;
+        s2 = warp_sum(s2) * inv_n;
+        TDx* dxr = dx + (size_t)row * cols;
+        for (int i = lane * 4; i < cols; i += 128) {
+            float4 xh = ld4(sx + i), d = ld4(sg + i), g = ld4(gamma + i);
+            float4 o;
+            o.x = rstd * (g.x * d.x - s1 - xh.x * s2);
+            o.y = rstd * (g.y * d.y - s1 - xh.y * s2);
+            o.z = rstd * (g.z * d.z - s1 - xh.z * s2);
+            o.w = rstd * (g.w * d.w - s1 - xh.w * s2);
+            if (dres != nullptr) {
+                float4 r = ld4(dres + (size_t)row * cols + i);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            st4(dxr + i, o);
+            // dgamma / dbeta: shared-memory accumulation (one atomic per element per row per CTA)
+            atomicAdd(&sdg[i + 0], d.x * xh.x); atomicAdd(&sdg[i + 1], d.y * xh.y);
+            atomicAdd(&sdg[i + 2], d.z * xh.z); atomicAdd(&sdg[i + 3], d.w * xh.w);
+            atomicAdd(&sdb[i + 0], d.x); atomicAdd(&sdb[i + 1], d.y);
+            atomicAdd(&sdb[i + 2], d.z); atomicAdd(&sdb[i + 3], d.w);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    float* pout = partials + (size_t)blockIdx.x * 2 * cols;
+    for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) pout[i] = sdg[i];
+}
+
+__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int cols,
+                                       __nv_bfloat16* __restrict__ dgamma, __nv_bfloat16* __restrict__ dbeta) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * cols) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * 2 * cols + i];
+    if (i < cols) dgamma[i] = __float2bfloat16_rn(s);
+    else dbeta[i - cols] = __float2bfloat16_rn(s);
+}
+
+int fwd_grid(int rows) {
+    int blocks = (rows + WARPS - 1) / WARPS;
+    int cap = cvh::num_sms() * 4;
+    return blocks < cap ? blocks : cap;
+}
+
+}  // namespace
+
+extern "C" int cv_layernorm_absmax_fwd(const void* x, int x_is_bf16, const float* absmax_in, const void* gamma,
+                                       const void* beta, float eps, const float* residual, void* out,
+                                       int out_is_bf16, float* absmax_out, float* mean_out, float* rstd_out,
+                                       int rows, int cols, void* stream) {
+    CV_REQUIRE(x && absmax_in && gamma && beta && out, "null pointer");
+    CV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
+    CV_REQUIRE((mean_out == nullptr) == (rstd_out == nullptr), "mean_out and rstd_out go together");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)WARPS * cols * sizeof(float);
+    CV_REQUIRE(smem <= 200 * 1024, "hidden size too large for the row cache");
+    const int grid = fwd_grid(rows);
+    const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gamma);
+    const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(beta);
+#define LAUNCH(TI, TO, RES)                                                                                    \
+    do {                                                                                                       \
+        auto k = ln_fwd_kernel<TI, TO, RES>;                                                                   \
+        CV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        k<<<grid, WARPS * 32, smem, s>>>(static_cast<const TI*>(x), absmax_in, g, b, eps, residual,            \
+                                         static_cast<TO*>(out), absmax_out, mean_out, rstd_out, rows, cols);   \
+    } while (0)
+    const bool res = residual != nullptr;
+    if (!x_is_bf16 && out_is_bf16 && !res) LAUNCH(float, __nv_bfloat16, false);
+    else if (x_is_bf16 && !out_is_bf16 && res) LAUNCH(__nv_bfloat16, float, true);
+    else if (x_is_bf16 && out_is_bf16 && !res) LAUNCH(__nv_bfloat16, __nv_bfloat16, false);
+    else if (!x_is_bf16 && !out_is_bf16 && !res) LAUNCH(float, float, false);
+    else if (!x_is_bf16 && !out_is_bf16 && res) LAUNCH(float, float, true);
+    else return cvh::fail_arg(__func__, "unsupported dtype/residual combination");
+#undef LAUNCH
+    CV_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t cv_layernorm_bwd_workspace_bytes(int rows, int cols) {
+    return (int64_t)fwd_grid(rows) * 2 * cols * sizeof(float);
+}
+
+extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16,
+                                       const float* mean, const float* rstd, const void* gamma, const float* dres,
+                                       void* dx, int dx_is_bf16, void* dgamma, void* dbeta, float* workspace,
+                                       int rows, int cols, void* stream) {
+    CV_REQUIRE(x && dy && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "null pointer");
+    CV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t smem = ((size_t)WARPS * 2 + 2) * cols * sizeof(float);
+    CV_REQUIRE(smem <= 220 * 1024, "hidden size too large for the row cache");
+    const int grid = fwd_grid(rows);
+    const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gamma);
+#define LAUNCH(TI, TDY, TDX)                                                                                   \
+    do {                                                                                                       \
+        auto k = ln_bwd_kernel<TI, TDY, TDX>;                                                                  \
+        CV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        k<<<grid, WARPS * 32, smem, s>>>(static_cast<const TI*>(x), static_cast<const TDY*>(dy), mean, rstd, g, \
+                                         dres, static_cast<TDX*>(dx), workspace, rows, cols);                  \
+    } while (0)
+    if (x_is_bf16 && !dy_is_bf16 && dx_is_bf16) LAUNCH(__nv_bfloat16, float, __nv_bfloat16);       // third/fourth LN
+    else if (!x_is_bf16 && dy_is_bf16 && !dx_is_bf16) LAUNCH(float, __nv_bfloat16, float);         // input/post/final LN
+    else if (!x_is_bf16 && !dy_is_bf16 && !dx_is_bf16) LAUNCH(float, float, float);
+    else if (x_is_bf16 && dy_is_bf16 && dx_is_bf16) LAUNCH(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
+    else return cvh::fail_arg(__func__, "unsupported dtype combination");
+#undef LAUNCH
+    CV_LAUNCH_CHECK();
+    const int n = 2 * cols;
+    ln_bwd_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(workspace, grid, cols, static_cast<__nv_bfloat16*>(dgamma),
+                                                          static_cast<__nv_bfloat16*>(dbeta));
+    CV_LAUNCH_CHECK();
+    return 0;
+}
