@@ -29,6 +29,23 @@ def _declare(lib):
         "cv_gemm_bf16": [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p,
                          c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     }
+    P, I, L, F = c_void_p, c_int, c_int64, c_float
+    sigs.update({
+        "cv_layernorm_absmax_fwd": [P, I, P, P, P, F, P, P, I, P, P, P, I, I, P],
+        "cv_layernorm_absmax_bwd": [P, I, P, I, P, P, P, P, P, I, P, P, P, I, I, P],
+        "cv_absmax": [P, I, L, P, P],
+        "cv_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, P],
+        "cv_embed_fwd": [P, P, P, P, P, P, I, I, P],
+        "cv_embed_bwd": [P, P, P, P, P, I, I, P],
+        "cv_cross_entropy_fwd": [P, L, P, P, P, P, I, I, P],
+        "cv_cross_entropy_bwd": [P, L, P, P, P, P, P, L, I, I, P],
+        "cv_gelu_bwd": [P, P, P, L, P],
+        "cv_colsum_bf16": [P, L, P, P, I, I, P],
+    })
+    lib.cv_layernorm_bwd_workspace_bytes.argtypes = [I, I]
+    lib.cv_layernorm_bwd_workspace_bytes.restype = L
+    lib.cv_colsum_workspace_bytes.argtypes = [I]
+    lib.cv_colsum_workspace_bytes.restype = L
     for name, args in sigs.items():
         fn = getattr(lib, name)
         fn.argtypes = args

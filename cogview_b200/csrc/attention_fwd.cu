@@ -1,0 +1,317 @@
+// cv_attn_fwd: fused dense attention forward (flash-style, nothing of size [sq, sk] ever reaches HBM).
+//
+// Replaces standard_attention (/root/reference/mpu/sparse_transformer.py:652-673) together with the
+// split / head-permute copies around it in GPT2ParallelSelfAttention.forward (:131-163):
+//     softmax( (Q / sqrt(hn)) K^T * mask - 10000 * (1 - mask) ) V
+// for the two mask families the reference builds: lower-triangular (pretrain_gpt2.py:218-221) and the
+// int-`sep` form (mpu/sparse_transformer.py:477-489: keys [0, sep + mem) visible to every query, causal
+// after that), with sq <= sk (queries are the LAST sq positions of the sk keys: decode-with-memory prefill).
+// Masked scores are exactly -10000 as in the reference; whole key tiles that are masked for every query
+// of the block are skipped (their softmax weight underflows to 0 in fp32).
+//
+// Q, K, V are read in place from the packed QKV GEMM output [b, s, 3h] (or a KV cache) through 3-D TMA
+// tensor maps; the context is written token-major [b, sq, h] — the layout the out-projection GEMM reads.
+//
+// One CTA per (128-query block, head, batch); 6 warps:
+//   warp 0     TMA producer (Q once; K/V tiles of 128 keys through a 3-stage ring)
+//   warp 1     tcgen05.mma issuer:  S = Q K^T (128x128x64) into TMEM;  O_j = P_j V_j (128x64x128) into TMEM
+//   warps 2-5  softmax: one thread per query row; tcgen05.ld S, online max/sum, P (bf16) -> swizzled smem,
+//              then accumulate O_j from TMEM into registers with the running rescale
+// S and O are double-buffered in TMEM so S_{j+1} is computed while the softmax of tile j runs.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/cogview_b200.h"
+
+namespace {
+using namespace cv;
+
+constexpr int BQ = 128;       // queries per CTA
+constexpr int BKV = 128;      // keys per tile
+constexpr int HD = 64;        // head dim (CogView: 2560 / 40)
+constexpr int KV_STAGES = 3;
+constexpr int Q_BYTES = BQ * HD * 2;        // 16 KB
+constexpr int K_BYTES = BKV * HD * 2;       // 16 KB
+constexpr int V_BYTES = BKV * HD * 2;       // 16 KB
+constexpr int P_BYTES = BQ * BKV * 2;       // 32 KB (two 128x64 K-major sub-tiles)
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
+constexpr int NUM_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnParams {
+    int b, heads, sq, sk;
+    int sep_eff;        // keys [0, sep_eff) are visible to every query
+    int off;            // sk - sq: query i sees key j <= i + off
+    float scale_log2;   // (1/sqrt(hn)) * log2(e)
+    __nv_bfloat16* out; // [b, sq, heads*HD]
+    int64_t ldo;        // row stride of out (elements)
+    int64_t bso;        // batch stride of out (elements)
+    float* lse;         // [b, heads, sq] natural-log LSE, or null
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = sQ + Q_BYTES;                              // stage s: K at s*(K+V), V after it
+    uint8_t* sP = sKV + KV_STAGES * (K_BYTES + V_BYTES);      // 2 buffers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+    uint64_t* q_full = bars;                 // [1]
+    uint64_t* kv_full = bars + 1;            // [KV_STAGES]
+    uint64_t* kv_empty = kv_full + KV_STAGES;
+    uint64_t* s_full = kv_empty + KV_STAGES; // [2]
+    uint64_t* p_full = s_full + 2;           // [2]
+    uint64_t* o_full = p_full + 2;           // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // heaviest (last) query blocks first
+    const int qb = gridDim.x - 1 - blockIdx.x;
+    const int head = blockIdx.y, batch = blockIdx.z;
+    const int q0 = qb * BQ;
+    // number of key tiles any query of this block can see
+    int kmax = q0 + BQ + p.off;              // exclusive bound of causally visible keys for the last row
+    if (kmax < p.sep_eff) kmax = p.sep_eff;
+    if (kmax > p.sk) kmax = p.sk;
+    const int nkb = (kmax + BKV - 1) / BKV;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t TM_S = 0, TM_O = 256;     // column offsets: S0, S1 (128 each); O0, O1 (64 each)
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, Q_BYTES);
+            tma_load_3d(sQ, &tmQ, q_full, head * HD, q0, batch);
+            int stage = 0; uint32_t phase = 0;
+            for (int j = 0; j < nkb; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                uint8_t* sK = sKV + stage * (K_BYTES + V_BYTES);
+                mbar_expect_tx(&kv_full[stage], K_BYTES + V_BYTES);
+                tma_load_3d(sK, &tmK, &kv_full[stage], head * HD, j * BKV, batch);
+                tma_load_3d(sK + K_BYTES, &tmV, &kv_full[stage], head * HD, j * BKV, batch);
+                if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // Q K-major, K K-major
+            constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);   // P K-major, V MN-major
+            const uint32_t q_addr = smem_u32(sQ);
+            auto issue_s = [&](int j, int stage) {
+                const uint32_t k_addr = smem_u32(sKV + stage * (K_BYTES + V_BYTES));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    umma_f16(tmem_base + TM_S + (j & 1) * BKV, make_smem_desc_sw128(q_addr + k * 32, 0, 1024),
+                             make_smem_desc_sw128(k_addr + k * 32, 0, 1024), idesc_s, k != 0);
+                }
+                umma_commit(&s_full[j & 1]);
+            };
+            mbar_wait(q_full, 0);
+            int ld_stage = 0; uint32_t ld_phase = 0;   // stage/phase of the next tile whose S is issued
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            ld_stage = 1 % KV_STAGES;
+            int pv_stage = 0;
+            for (int j = 0; j < nkb; ++j) {
+                if (j + 1 < nkb) {
+                    mbar_wait(&kv_full[ld_stage], ld_phase);
+                    tc_fence_after();
+                    issue_s(j + 1, ld_stage);
+                    if (++ld_stage == KV_STAGES) { ld_stage = 0; ld_phase ^= 1; }
+                }
+                mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t p_addr = smem_u32(sP + (j & 1) * P_BYTES);
+                const uint32_t v_addr = smem_u32(sKV + pv_stage * (K_BYTES + V_BYTES) + K_BYTES);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    const uint32_t pa = p_addr + (k >> 2) * (BQ * 128) + (k & 3) * 32;
+                    umma_f16(tmem_base + TM_O + (j & 1) * HD, make_smem_desc_sw128(pa, 0, 1024),
+                             make_smem_desc_sw128(v_addr + k * (16 * 128), BKV * 128, 1024), idesc_o, k != 0);
+                }
+                umma_commit(&o_full[j & 1]);
+                umma_commit(&kv_empty[pv_stage]);
+                if (++pv_stage == KV_STAGES) pv_stage = 0;
+            }
+        }
+    } else {
+        // ------------------------------ softmax / output warps ------------------------------
+        const int q = warp_idx & 3;
+        const int row = q * 32 + lane;
+        const int qi = q0 + row;                       // query index within the sequence
+        const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+        const int causal_lim = qi + p.off;             // last causally visible key
+        float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+        float o[HD];
+#pragma unroll
+        for (int i = 0; i < HD; ++i) o[i] = 0.f;
+        const float masked_val = -10000.0f * LOG2E;
+
+        for (int j = 0; j < nkb; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            const int k0 = j * BKV;
+            // does this tile need per-element masking for this row?
+            const bool full_vis = (k0 + BKV <= p.sk) && ((k0 + BKV <= p.sep_eff) || (k0 + BKV - 1 <= causal_lim));
+            float s[BKV];
+#pragma unroll
+            for (int c = 0; c < BKV / 32; ++c) {
+                uint32_t (&r)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
+                tmem_ld_x32(lane_addr + TM_S + (j & 1) * BKV + c * 32, r);
+            }
+            tmem_ld_wait();
+            float mx = m;
+            if (full_vis) {
+#pragma unroll
+                for (int i = 0; i < BKV; ++i) { s[i] *= p.scale_log2; mx = fmaxf(mx, s[i]); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < BKV; ++i) {
+                    const int kj = k0 + i;
+                    const bool vis = (kj < p.sep_eff) || (kj <= causal_lim);
+                    float v = vis ? s[i] * p.scale_log2 : masked_val;
+                    if (kj >= p.sk) v = -INFINITY;     // key does not exist
+                    s[i] = v;
+                    mx = fmaxf(mx, v);
+                }
+            }
+            const float alpha = exp2f(m - mx);          // m = -inf on the first tile -> 0
+            m = mx;
+            float psum = 0.f;
+            uint8_t* prow = sP + (j & 1) * P_BYTES + row * 128;
+#pragma unroll
+            for (int c = 0; c < BKV / 8; ++c) {         // 16 chunks of 8 keys (16 bytes)
+                float e[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) e[t] = exp2f(s[c * 8 + t] - mx);
+                uint4 pk;
+                pk.x = pack_bf16x2(e[0], e[1]); pk.y = pack_bf16x2(e[2], e[3]);
+                pk.z = pack_bf16x2(e[4], e[5]); pk.w = pack_bf16x2(e[6], e[7]);
+                // the row sum uses the bf16-rounded probabilities that the PV MMA will see
+                const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) psum += __low2float(pb[t]) + __high2float(pb[t]);
+                const int sub = c >> 3, cc = c & 7;     // sub-tile of 64 keys, 16-byte chunk within the 128 B row
+                *reinterpret_cast<uint4*>(prow + sub * (BQ * 128) + ((cc ^ (row & 7)) << 4)) = pk;
+            }
+            l = l * alpha + psum;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&p_full[j & 1]);
+            if (j > 0) {
+                mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+                uint32_t r[HD];
+                {
+                    uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+                    uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+                    tmem_ld_x32(lane_addr + TM_O + ((j - 1) & 1) * HD, r0);
+                    tmem_ld_x32(lane_addr + TM_O + ((j - 1) & 1) * HD + 32, r1);
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < HD; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(r[i]);
+            }
+            alpha_prev = alpha;
+        }
+        {
+            const int j = nkb - 1;
+            mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t r[HD];
+            {
+                uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+                uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+                tmem_ld_x32(lane_addr + TM_O + (j & 1) * HD, r0);
+                tmem_ld_x32(lane_addr + TM_O + (j & 1) * HD + 32, r1);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < HD; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(r[i]);
+        }
+        if (qi < p.sq) {
+            const float inv_l = 1.0f / l;
+            __nv_bfloat16* orow = p.out + (size_t)batch * p.bso + (size_t)qi * p.ldo + head * HD;
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                uint4 pk;
+                pk.x = pack_bf16x2(o[c * 8 + 0] * inv_l, o[c * 8 + 1] * inv_l);
+                pk.y = pack_bf16x2(o[c * 8 + 2] * inv_l, o[c * 8 + 3] * inv_l);
+                pk.z = pack_bf16x2(o[c * 8 + 4] * inv_l, o[c * 8 + 5] * inv_l);
+                pk.w = pack_bf16x2(o[c * 8 + 6] * inv_l, o[c * 8 + 7] * inv_l);
+                *reinterpret_cast<uint4*>(orow + c * 8) = pk;
+            }
+            if (p.lse != nullptr)
+                p.lse[((size_t)batch * p.heads + head) * p.sq + qi] = m * 0.6931471805599453f + logf(l);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// [b, s, cols] bf16 view: row stride ld, batch stride bs (elements); box [64 cols x box_rows rows x 1]
+int encode_qkv_map(CUtensorMap* m, const void* base, int b, int s, int cols, int64_t ld, int64_t bs, int box_rows) {
+    uint64_t dims[3] = {(uint64_t)cols, (uint64_t)s, (uint64_t)b};
+    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)bs * 2};
+    uint32_t box[3] = {64, (uint32_t)box_rows, 1};
+    return cvh::encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, str, box, nullptr, cvh::Swizzle::B128);
+}
+
+}  // namespace
+
+extern "C" int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                           const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, float* lse,
+                           int b, int heads, int head_dim, int sq, int sk, int sep, void* stream) {
+    CV_REQUIRE(q && k && v && out, "null pointer");
+    CV_REQUIRE(head_dim == HD, "head_dim must be 64 (CogView: hidden / heads = 64)");
+    CV_REQUIRE(b > 0 && heads > 0 && sq > 0 && sk >= sq, "need sk >= sq > 0");
+    CV_REQUIRE(sep >= 0 && sep <= sq, "sep must be in [0, sq]");
+    CV_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && bsq % 8 == 0 && bsk % 8 == 0 &&
+                   bsv % 8 == 0 && bso % 8 == 0,
+               "strides must be multiples of 8 elements");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    alignas(64) CUtensorMap tmQ, tmK, tmV;
+    int rc;
+    if ((rc = encode_qkv_map(&tmQ, q, b, sq, heads * HD, ldq, bsq, BQ))) return rc;
+    if ((rc = encode_qkv_map(&tmK, k, b, sk, heads * HD, ldk, bsk, BKV))) return rc;
+    if ((rc = encode_qkv_map(&tmV, v, b, sk, heads * HD, ldv, bsv, BKV))) return rc;
+    AttnParams p;
+    p.b = b; p.heads = heads; p.sq = sq; p.sk = sk;
+    p.off = sk - sq;
+    p.sep_eff = sep > 0 ? sep + (sk - sq) : 0;   // mpu/sparse_transformer.py:486; sep = 0 with memory: see below
+    // NB: with sep == 0 the reference still marks the memory columns [0, sk - sq) visible (:486 with sep = 0);
+    // they are causally visible anyway (j <= i + off for every i >= 0), so sep_eff = 0 is equivalent.
+    p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * LOG2E;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo; p.bso = bso;
+    p.lse = lse;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid((sq + BQ - 1) / BQ, heads, b);
+    attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
+    CV_LAUNCH_CHECK();
+    return 0;
+}

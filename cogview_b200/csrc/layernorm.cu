@@ -18,10 +18,8 @@ using namespace cv;
 
 constexpr int WARPS = 8;
 
-__device__ __forceinline__ float ld_as_float(const float* p, int i) { return p[i]; }
-__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p, int i) { return __bfloat162float(p[i]); }
-__device__ __forceinline__ void st_from_float(float* p, int i, float v) { p[i] = v; }
-__device__ __forceinline__ void st_from_float(__nv_bfloat16* p, int i, float v) { p[i] = __float2bfloat16_rn(v); }
+__device__ __forceinline__ float ld_as_float(const float* p, size_t i) { return p[i]; }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
 
 // vector loads of 4 consecutive elements
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -105,21 +103,15 @@ ln_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ absmax_in, co
 // Backward.  dy: gradient of the LN output (TDy); dres (optional fp32): gradient already flowing on the
 // residual path that must be added to dx (fp32 output) — used for the input/post-attention/final LNs.
 //   dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)),  xhat = (x - mean) * rstd
-// dgamma/dbeta partial sums per CTA go to `partials` [gridDim.x, 2, cols]; ln_bwd_finalize reduces them.
 template <typename TIn, typename TDy, typename TDx>
 __global__ void __launch_bounds__(WARPS * 32)
-ln_bwd_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const float* __restrict__ mean_in,
-              const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ gamma,
-              const float* __restrict__ dres, TDx* __restrict__ dx, float* __restrict__ partials, int rows,
-              int cols) {
+ln_bwd_dx_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const float* __restrict__ mean_in,
+                 const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ gamma,
+                 const float* __restrict__ dres, TDx* __restrict__ dx, int rows, int cols) {
     extern __shared__ float smem_f[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* sx = smem_f + (size_t)warp * 2 * cols;   // xhat
-    float* sg = sx + cols;                            // dy (raw)
-    float* sdg = smem_f + (size_t)WARPS * 2 * cols;   // [cols] dgamma accum (block-shared)
-    float* sdb = sdg + cols;
-    for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) sdg[i] = 0.f;
-    __syncthreads();
+    float* sg = sx + cols;                            // gamma * dy
     const float inv_n = 1.0f / cols;
     for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
         const float mean = mean_in[row], rstd = rstd_in[row];
@@ -129,38 +121,55 @@ ln_bwd_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const float
         for (int i = lane * 4; i < cols; i += 128) {
             float4 v = ld4(xr + i), d = ld4(dyr + i), g = ld4(gamma + i);
             float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+            float4 a = make_float4(g.x * d.x, g.y * d.y, g.z * d.z, g.w * d.w);
             st4(sx + i, xh);
-            st4(sg + i, d);
-            float a0 = g.x * d.x, a1 = g.y * d.y, a2 = g.z * d.z, a3 = g.w * d.w;
-            s1 += (a0 + a1) + (a2 + a3);
-            s2 += (a0 * xh.x + a1 * xh.y) + (a2 * xh.z + a3 * xh.w);
+            st4(sg + i, a);
+            s1 += (a.x + a.y) + (a.z + a.w);
+            s2 += (a.x * xh.x + a.y * xh.y) + (a.z * xh.z + a.w * xh.w);
         }
         s1 = warp_sum(s1) * inv_n;
         s2 = warp_sum(s2) * inv_n;
         TDx* dxr = dx + (size_t)row * cols;
         for (int i = lane * 4; i < cols; i += 128) {
-            float4 xh = ld4(sx + i), d = ld4(sg + i), g = ld4(gamma + i);
+            float4 xh = ld4(sx + i), a = ld4(sg + i);
             float4 o;
-            o.x = rstd * (g.x * d.x - s1 - xh.x * s2);
-            o.y = rstd * (g.y * d.y - s1 - xh.y * s2);
-            o.z = rstd * (g.z * d.z - s1 - xh.z * s2);
-            o.w = rstd * (g.w * d.w - s1 - xh.w * s2);
+            o.x = rstd * (a.x - s1 - xh.x * s2);
+            o.y = rstd * (a.y - s1 - xh.y * s2);
+            o.z = rstd * (a.z - s1 - xh.z * s2);
+            o.w = rstd * (a.w - s1 - xh.w * s2);
             if (dres != nullptr) {
                 float4 r = ld4(dres + (size_t)row * cols + i);
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
             }
             st4(dxr + i, o);
-            // dgamma / dbeta: shared-memory accumulation (one atomic per element per row per CTA)
-            atomicAdd(&sdg[i + 0], d.x * xh.x); atomicAdd(&sdg[i + 1], d.y * xh.y);
-            atomicAdd(&sdg[i + 2], d.z * xh.z); atomicAdd(&sdg[i + 3], d.w * xh.w);
-            atomicAdd(&sdb[i + 0], d.x); atomicAdd(&sdb[i + 1], d.y);
-            atomicAdd(&sdb[i + 2], d.z); atomicAdd(&sdb[i + 3], d.w);
         }
         __syncwarp();
     }
-    __syncthreads();
-    float* pout = partials + (size_t)blockIdx.x * 2 * cols;
-    for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) pout[i] = sdg[i];
+}
+
+// dgamma[c] = sum_r dy[r,c] * xhat[r,c], dbeta[c] = sum_r dy[r,c].  Thread per column (coalesced across columns),
+// rows split over blockIdx.y; partial sums go to `partials` [gridDim.y, 2, cols], reduced by ln_bwd_finalize.
+constexpr int PARAM_ROW_SPLITS = 32;
+template <typename TIn, typename TDy>
+__global__ void __launch_bounds__(128)
+ln_bwd_param_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const float* __restrict__ mean_in,
+                    const float* __restrict__ rstd_in, float* __restrict__ partials, int rows, int cols) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per;
+    const int r1 = min(rows, r0 + rows_per);
+    float dg = 0.f, db = 0.f;
+    if (c < cols) {
+#pragma unroll 4
+        for (int r = r0; r < r1; ++r) {
+            const float d = ld_as_float(dy, (size_t)r * cols + c);
+            const float xh = (ld_as_float(x, (size_t)r * cols + c) - mean_in[r]) * rstd_in[r];
+            dg += d * xh;
+            db += d;
+        }
+        partials[((size_t)blockIdx.y * 2 + 0) * cols + c] = dg;
+        partials[((size_t)blockIdx.y * 2 + 1) * cols + c] = db;
+    }
 }
 
 __global__ void ln_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int cols,
@@ -214,7 +223,8 @@ extern "C" int cv_layernorm_absmax_fwd(const void* x, int x_is_bf16, const float
 }
 
 extern "C" int64_t cv_layernorm_bwd_workspace_bytes(int rows, int cols) {
-    return (int64_t)fwd_grid(rows) * 2 * cols * sizeof(float);
+    (void)rows;
+    return (int64_t)PARAM_ROW_SPLITS * 2 * cols * sizeof(float);
 }
 
 extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16,
@@ -224,16 +234,20 @@ extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void*
     CV_REQUIRE(x && dy && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "null pointer");
     CV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t smem = ((size_t)WARPS * 2 + 2) * cols * sizeof(float);
+    const size_t smem = (size_t)WARPS * 2 * cols * sizeof(float);
     CV_REQUIRE(smem <= 220 * 1024, "hidden size too large for the row cache");
     const int grid = fwd_grid(rows);
     const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gamma);
+    const int splits = rows < PARAM_ROW_SPLITS ? rows : PARAM_ROW_SPLITS;
+    dim3 pgrid((cols + 127) / 128, splits);
 #define LAUNCH(TI, TDY, TDX)                                                                                   \
     do {                                                                                                       \
-        auto k = ln_bwd_kernel<TI, TDY, TDX>;                                                                  \
+        auto k = ln_bwd_dx_kernel<TI, TDY, TDX>;                                                               \
         CV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
         k<<<grid, WARPS * 32, smem, s>>>(static_cast<const TI*>(x), static_cast<const TDY*>(dy), mean, rstd, g, \
-                                         dres, static_cast<TDX*>(dx), workspace, rows, cols);                  \
+                                         dres, static_cast<TDX*>(dx), rows, cols);                             \
+        ln_bwd_param_kernel<TI, TDY><<<pgrid, 128, 0, s>>>(static_cast<const TI*>(x), static_cast<const TDY*>(dy), \
+                                                           mean, rstd, workspace, rows, cols);                  \
     } while (0)
     if (x_is_bf16 && !dy_is_bf16 && dx_is_bf16) LAUNCH(__nv_bfloat16, float, __nv_bfloat16);       // third/fourth LN
     else if (!x_is_bf16 && dy_is_bf16 && !dx_is_bf16) LAUNCH(float, __nv_bfloat16, float);         // input/post/final LN
@@ -243,7 +257,7 @@ extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void*
 #undef LAUNCH
     CV_LAUNCH_CHECK();
     const int n = 2 * cols;
-    ln_bwd_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(workspace, grid, cols, static_cast<__nv_bfloat16*>(dgamma),
+    ln_bwd_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(workspace, splits, cols, static_cast<__nv_bfloat16*>(dgamma),
                                                           static_cast<__nv_bfloat16*>(dbeta));
     CV_LAUNCH_CHECK();
     return 0;

@@ -43,3 +43,153 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, bias=None, act=ACT_NONE, o
                             ptr(absmax), M, N, K, block_n, stream_ptr())
     check(rc, "cv_gemm_bf16")
     return (out, pre) if want_preact else out
+
+
+# ----------------------------------------------------------------------------------------------------
+# abs-max LayerNorm
+# ----------------------------------------------------------------------------------------------------
+def new_scalars(n, device):
+    """n zero-initialised fp32 scalars (abs-max accumulators must start at a non-negative value)."""
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+def absmax(x, out=None):
+    require_cuda(x)
+    x = x.contiguous()
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float32, device=x.device)
+    assert x.dtype in (torch.float32, torch.bfloat16)
+    check(lib().cv_absmax(ptr(x), int(x.dtype == torch.bfloat16), x.numel(), ptr(out), stream_ptr()), "cv_absmax")
+    return out
+
+
+def layernorm_absmax_fwd(x, absmax_in, gamma, beta, eps, *, residual=None, out_dtype=torch.bfloat16,
+                         absmax_out=None, save_stats=False):
+    """x: [rows, cols] fp32|bf16 contiguous.  Returns (out, mean, rstd) (stats None unless save_stats)."""
+    require_cuda(x, absmax_in, gamma, beta, residual)
+    assert x.is_contiguous() and x.dim() == 2
+    rows, cols = x.shape
+    assert gamma.dtype == torch.bfloat16 and beta.dtype == torch.bfloat16
+    out = torch.empty((rows, cols), dtype=out_dtype, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
+    rc = lib().cv_layernorm_absmax_fwd(ptr(x), int(x.dtype == torch.bfloat16), ptr(absmax_in), ptr(gamma), ptr(beta),
+                                       float(eps), ptr(residual), ptr(out), int(out_dtype == torch.bfloat16),
+                                       ptr(absmax_out), ptr(mean), ptr(rstd), rows, cols, stream_ptr())
+    check(rc, "cv_layernorm_absmax_fwd")
+    return out, mean, rstd
+
+
+def layernorm_absmax_bwd(x, dy, mean, rstd, gamma, *, dres=None, dx_dtype=torch.float32):
+    """Returns (dx, dgamma, dbeta)."""
+    require_cuda(x, dy, mean, rstd, gamma, dres)
+    assert x.is_contiguous() and dy.is_contiguous()
+    rows, cols = x.shape
+    dx = torch.empty((rows, cols), dtype=dx_dtype, device=x.device)
+    dgamma = torch.empty(cols, dtype=torch.bfloat16, device=x.device)
+    dbeta = torch.empty(cols, dtype=torch.bfloat16, device=x.device)
+    ws = torch.empty(lib().cv_layernorm_bwd_workspace_bytes(rows, cols) // 4, dtype=torch.float32, device=x.device)
+    if dres is not None:
+        assert dres.dtype == torch.float32 and dres.is_contiguous()
+    rc = lib().cv_layernorm_absmax_bwd(ptr(x), int(x.dtype == torch.bfloat16), ptr(dy),
+                                       int(dy.dtype == torch.bfloat16), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres),
+                                       ptr(dx), int(dx_dtype == torch.bfloat16), ptr(dgamma), ptr(dbeta), ptr(ws),
+                                       rows, cols, stream_ptr())
+    check(rc, "cv_layernorm_absmax_bwd")
+    return dx, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------
+def attn_fwd(q, k, v, heads, *, sep=0, want_lse=False):
+    """q: [b, sq, heads*64] view, k/v: [b, sk, heads*64] views (last dim contiguous, bf16).
+    Returns ctx [b, sq, heads*64] bf16 (and lse [b, heads, sq] fp32)."""
+    require_cuda(q, k, v)
+    b, sq, hq = q.shape
+    sk = k.shape[1]
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    assert hq == heads * 64 and k.shape[2] == hq and v.shape == k.shape
+    out = torch.empty((b, sq, hq), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((b, heads, sq), dtype=torch.float32, device=q.device) if want_lse else None
+    rc = lib().cv_attn_fwd(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
+                           v.stride(0), ptr(out), out.stride(1), out.stride(0), ptr(lse), b, heads, 64, sq, sk,
+                           int(sep), stream_ptr())
+    check(rc, "cv_attn_fwd")
+    return (out, lse) if want_lse else out
+
+
+# ----------------------------------------------------------------------------------------------------
+# embedding, cross-entropy, small backward helpers
+# ----------------------------------------------------------------------------------------------------
+def embed_fwd(ids, pos, wte, wpe, absmax_out=None):
+    require_cuda(ids, pos, wte, wpe)
+    ids = ids.contiguous().view(-1)
+    pos = pos.contiguous().view(-1)
+    assert ids.dtype == torch.int64 and pos.dtype == torch.int64 and ids.numel() == pos.numel()
+    assert wte.dtype == torch.bfloat16 and wpe.dtype == torch.bfloat16 and wte.is_contiguous() and wpe.is_contiguous()
+    h = wte.shape[1]
+    out = torch.empty((ids.numel(), h), dtype=torch.float32, device=wte.device)
+    check(lib().cv_embed_fwd(ptr(ids), ptr(pos), ptr(wte), ptr(wpe), ptr(out), ptr(absmax_out), ids.numel(), h,
+                             stream_ptr()), "cv_embed_fwd")
+    return out
+
+
+def embed_bwd(ids, pos, dx, dwte, dwpe):
+    """Accumulates into dwte / dwpe (bf16, contiguous)."""
+    require_cuda(ids, pos, dx, dwte, dwpe)
+    ids = ids.contiguous().view(-1)
+    pos = pos.contiguous().view(-1)
+    assert dx.dtype == torch.float32 and dx.is_contiguous()
+    check(lib().cv_embed_bwd(ptr(ids), ptr(pos), ptr(dx), ptr(dwte), ptr(dwpe), ids.numel(), dwte.shape[1],
+                             stream_ptr()), "cv_embed_bwd")
+
+
+def cross_entropy_fwd(logits, target):
+    """logits: [rows, V] fp32 (last dim contiguous); target int64 [rows].  Returns (loss, row_max, row_sum)."""
+    require_cuda(logits, target)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    rows, V = logits.shape
+    target = target.contiguous().view(-1)
+    assert target.numel() == rows and target.dtype == torch.int64
+    loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    rmax = torch.empty_like(loss)
+    rsum = torch.empty_like(loss)
+    check(lib().cv_cross_entropy_fwd(ptr(logits), logits.stride(0), ptr(target), ptr(loss), ptr(rmax), ptr(rsum), rows,
+                                     V, stream_ptr()), "cv_cross_entropy_fwd")
+    return loss, rmax, rsum
+
+
+def cross_entropy_bwd(logits, target, rmax, rsum, grad_loss):
+    require_cuda(logits, target, grad_loss)
+    rows, V = logits.shape
+    target = target.contiguous().view(-1)
+    grad_loss = grad_loss.contiguous().view(-1).float()
+    ldd = (V + 7) // 8 * 8
+    dl = torch.empty((rows, ldd), dtype=torch.bfloat16, device=logits.device)
+    check(lib().cv_cross_entropy_bwd(ptr(logits), logits.stride(0), ptr(target), ptr(rmax), ptr(rsum), ptr(grad_loss),
+                                     ptr(dl), ldd, rows, V, stream_ptr()), "cv_cross_entropy_bwd")
+    return dl[:, :V]
+
+
+def gelu_bwd(pre, dact):
+    require_cuda(pre, dact)
+    assert pre.is_contiguous() and dact.is_contiguous() and pre.dtype == torch.bfloat16 and dact.dtype == torch.bfloat16
+    out = torch.empty_like(pre)
+    check(lib().cv_gelu_bwd(ptr(pre), ptr(dact), ptr(out), pre.numel(), stream_ptr()), "cv_gelu_bwd")
+    return out
+
+
+def colsum(dy):
+    """bias gradient: sum over rows of a [rows, cols] bf16 matrix -> [cols] bf16."""
+    require_cuda(dy)
+    assert dy.dim() == 2 and dy.stride(1) == 1 and dy.dtype == torch.bfloat16
+    rows, cols = dy.shape
+    out = torch.empty(cols, dtype=torch.bfloat16, device=dy.device)
+    ws = torch.empty(lib().cv_colsum_workspace_bytes(cols) // 4, dtype=torch.float32, device=dy.device)
+    check(lib().cv_colsum_bf16(ptr(dy), dy.stride(0), ptr(out), ptr(ws), rows, cols, stream_ptr()), "cv_colsum_bf16")
+    return out

@@ -44,6 +44,66 @@ int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int 
                  void* C, int c_is_f32, int64_t ldc, void* C2, const void* bias, int act, float* absmax,
                  int M, int N, int K, int block_n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Abs-max pre-scaled LayerNorm: y = LN(x / (max|x|/8)) * gamma + beta (+ residual)
+ *   replaces mpu.LayerNorm.forward (mpu/sparse_transformer.py:40-44) = x.abs().max(), div, apex FusedLayerNorm;
+ *   with `residual` it also performs the Sandwich-LN residual add (mpu/sparse_transformer.py:326-329, :337-340).
+ *   absmax_in : device float holding max|x| (written by the kernel that produced x, or by cv_absmax)
+ *   absmax_out: NULL or device float (>= 0) receiving atomic max |out| (for the next LayerNorm)
+ *   mean_out/rstd_out: NULL or [rows] fp32 saved for the backward
+ *   supported (x, out, residual): (f32,bf16,-) (bf16,f32,res) (bf16,bf16,-) (f32,f32,-) (f32,f32,res)
+ * ---------------------------------------------------------------------------------------------- */
+int cv_layernorm_absmax_fwd(const void* x, int x_is_bf16, const float* absmax_in, const void* gamma,
+                            const void* beta, float eps, const float* residual, void* out, int out_is_bf16,
+                            float* absmax_out, float* mean_out, float* rstd_out, int rows, int cols, void* stream);
+int64_t cv_layernorm_bwd_workspace_bytes(int rows, int cols);
+/* dx = LN'(dy) (+ dres); dgamma/dbeta bf16 [cols]; workspace of cv_layernorm_bwd_workspace_bytes() bytes.
+ * The abs-max scale is a detached constant in the reference (x.abs().max().detach()), and so it is here. */
+int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, const float* mean,
+                            const float* rstd, const void* gamma, const float* dres, void* dx, int dx_is_bf16,
+                            void* dgamma, void* dbeta, float* workspace, int rows, int cols, void* stream);
+int cv_absmax(const void* x, int x_is_bf16, int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense attention forward: ctx = softmax((Q/sqrt(hn)) K^T * mask - 10000 (1 - mask)) V
+ *   replaces standard_attention (mpu/sparse_transformer.py:652-673) and the split/permute/contiguous copies
+ *   of GPT2ParallelSelfAttention.forward (mpu/sparse_transformer.py:131-163).
+ *   q: [b, sq, heads*64], k/v: [b, sk, heads*64] bf16 with row stride ld* and batch stride bs* (elements) —
+ *   e.g. three views into the packed QKV GEMM output.  Queries are the LAST sq of the sk positions.
+ *   mask: key j visible to query i iff j < sep + (sk - sq) or j <= i + (sk - sq)
+ *         (sep = 0: lower-triangular mask of pretrain_gpt2.py:218-221; sep > 0: the int-`sep` form of
+ *          mpu/sparse_transformer.py:477-489)
+ *   out: [b, sq, heads*64] bf16 (token-major, what the out-projection GEMM reads); lse: NULL or [b, heads, sq]
+ * ---------------------------------------------------------------------------------------------- */
+int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
+                int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, float* lse, int b, int heads,
+                int head_dim, int sq, int sk, int sep, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embedding: hidden = wte[ids] + wpe[pos] (fp32) and max|hidden|
+ *   replaces VocabParallelEmbedding.forward (mpu/layers.py:117-133) + position add (mpu/sparse_transformer.py:522-523)
+ * ---------------------------------------------------------------------------------------------- */
+int cv_embed_fwd(const int64_t* ids, const int64_t* pos, const void* wte, const void* wpe, float* out,
+                 float* absmax, int rows, int hidden, void* stream);
+int cv_embed_bwd(const int64_t* ids, const int64_t* pos, const float* dx, void* dwte, void* dwpe, int rows,
+                 int hidden, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Vocab cross-entropy on fp32 logits — mpu/cross_entropy.py:27-104 at model-parallel size 1.
+ *   fwd: loss[r], and the row max / sum(exp) saved for bwd;  bwd: dlogits (bf16) = (softmax - onehot) * grad_loss[r]
+ * ---------------------------------------------------------------------------------------------- */
+int cv_cross_entropy_fwd(const float* logits, int64_t ld, const int64_t* target, float* loss, float* row_max,
+                         float* row_sum, int rows, int vocab, void* stream);
+int cv_cross_entropy_bwd(const float* logits, int64_t ld, const int64_t* target, const float* row_max,
+                         const float* row_sum, const float* grad_loss, void* dlogits, int64_t ldd, int rows,
+                         int vocab, void* stream);
+
+/* GELU backward (mpu/sparse_transformer.py:172-176): dpre = dact * gelu'(pre), bf16, n % 8 == 0 */
+int cv_gelu_bwd(const void* pre, const void* dact, void* dpre, int64_t n, void* stream);
+/* bias gradient: out[c] = sum_r dy[r, c] (bf16 in/out, fp32 accumulate) */
+int64_t cv_colsum_workspace_bytes(int cols);
+int cv_colsum_bf16(const void* dy, int64_t ld, void* out, float* workspace, int rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

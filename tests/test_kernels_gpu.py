@@ -1,0 +1,159 @@
+"""GPU parity tests of the individual C-ABI kernels against the CPU oracle (oracle/cogview_oracle.py) on
+seeded inputs.  Tolerances: bf16 outputs are compared at 2e-2 of the tensor scale (bf16 has 8 mantissa
+bits; inputs are rounded to bf16 before the oracle sees them, so only accumulation order and the final
+rounding differ); fp32 outputs at 1e-4."""
+import math
+
+import pytest
+import torch
+
+from oracle import cogview_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from cogview_b200 import ops as _ops
+    return _ops
+
+
+def rel_err(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(256, 768, 256, 0, 0), (200, 328, 136, 0, 0), (256, 256, 1024, 0, 1),
+                                             (256, 1024, 256, 1, 1), (4352, 2560, 2560, 0, 0)])
+def test_gemm_matches_fp32_matmul(ops, M, N, K, a_mn, b_mn):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = bf(torch.randn((K, M) if a_mn else (M, K), generator=g))
+    B = bf(torch.randn((K, N) if b_mn else (N, K), generator=g))
+    bias = bf(torch.randn(N, generator=g))
+    ref = (A.float().t() if a_mn else A.float()) @ (B.float() if b_mn else B.float().t()) + bias.float()
+    out = ops.gemm(A.cuda(), B.cuda(), a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), bias=bias.cuda())
+    assert rel_err(out, ref) < 1e-2
+    out32 = ops.gemm(A.cuda(), B.cuda(), a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), bias=bias.cuda(),
+                     out_dtype=torch.float32)
+    assert rel_err(out32, ref) < 1e-4
+
+
+def test_gemm_gelu_preact_absmax(ops):
+    g = torch.Generator().manual_seed(3)
+    A, B, bias = bf(torch.randn((384, 256), generator=g)), bf(torch.randn((1024, 256), generator=g) * 0.1), bf(
+        torch.randn(1024, generator=g))
+    pre_ref = A.float() @ B.float().t() + bias.float()
+    act_ref = O.gelu(pre_ref)
+    am = torch.zeros(1, device="cuda")
+    out, pre = ops.gemm(A.cuda(), B.cuda(), bias=bias.cuda(), act=ops.ACT_GELU, absmax=am, want_preact=True)
+    assert rel_err(pre, pre_ref) < 1e-2 and rel_err(out, act_ref) < 1e-2
+    assert am.item() == out.float().abs().max().item()
+
+
+@pytest.mark.parametrize("rows,cols", [(256, 256), (100, 2560)])
+def test_layernorm_absmax_fwd_bwd(ops, rows, cols):
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn((rows, cols), generator=g) * 3.0
+    x[0, 0] = 40.0                                    # an outlier sets the global scale
+    gamma, beta = bf(1 + 0.1 * torch.randn(cols, generator=g)), bf(0.1 * torch.randn(cols, generator=g))
+    res = torch.randn((rows, cols), generator=g)
+    # (1) fp32 in -> bf16 out (input / post-attention / final LN)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.float().requires_grad_(True), beta.float().requires_grad_(True)
+    y_ref = O.layernorm_absmax(xr, gr, br)
+    am = ops.absmax(x.cuda())
+    assert am.item() == x.abs().max().item()
+    y, mean, rstd = ops.layernorm_absmax_fwd(x.cuda(), am, gamma.cuda(), beta.cuda(), 1e-5, save_stats=True)
+    assert rel_err(y, y_ref.detach()) < 1e-2
+    dy = bf(torch.randn((rows, cols), generator=g))
+    dres = torch.randn((rows, cols), generator=g)
+    y_ref.backward(dy.float())
+    dx, dg, db = ops.layernorm_absmax_bwd(x.cuda(), dy.cuda(), mean, rstd, gamma.cuda(), dres=dres.cuda())
+    assert rel_err(dx, xr.grad + dres) < 1e-4
+    assert rel_err(dg, gr.grad) < 1e-2 and rel_err(db, br.grad) < 1e-2
+    # (2) bf16 in -> fp32 out with residual (third / fourth LN), abs-max of the result
+    xb = bf(x)
+    xr2 = xb.float().requires_grad_(True)
+    y2_ref = res + O.layernorm_absmax(xr2, gamma.float(), beta.float())
+    am2, amo = ops.absmax(xb.cuda()), torch.zeros(1, device="cuda")
+    y2, mean2, rstd2 = ops.layernorm_absmax_fwd(xb.cuda(), am2, gamma.cuda(), beta.cuda(), 1e-5, residual=res.cuda(),
+                                                out_dtype=torch.float32, absmax_out=amo, save_stats=True)
+    assert rel_err(y2, y2_ref.detach()) < 1e-4
+    assert abs(amo.item() - y2.abs().max().item()) == 0.0
+    dy2 = torch.randn((rows, cols), generator=g)
+    y2_ref.backward(dy2)
+    dx2, _, _ = ops.layernorm_absmax_bwd(xb.cuda(), dy2.cuda(), mean2, rstd2, gamma.cuda(), dx_dtype=torch.bfloat16)
+    assert rel_err(dx2, xr2.grad) < 1e-2
+
+
+@pytest.mark.parametrize("b,heads,sq,sk,sep", [(2, 4, 128, 128, 0), (2, 3, 200, 200, 0), (1, 2, 1088, 1088, 0),
+                                               (2, 2, 128, 128, 40), (2, 2, 72, 200, 0), (1, 2, 300, 300, 130)])
+def test_attention_fwd_matches_standard_attention(ops, b, heads, sq, sk, sep):
+    g = torch.Generator().manual_seed(sq + sk + sep)
+    h = heads * 64
+    qkv_q = bf(torch.randn((b, sq, h), generator=g))
+    kv = bf(torch.randn((b, sk, 2 * h), generator=g))
+    k, v = kv[..., :h], kv[..., h:]
+
+    def heads_of(t):
+        return t.float().view(t.shape[0], t.shape[1], heads, 64).permute(0, 2, 1, 3)
+
+    mask = O.build_sep_mask(sq, sk, sep)
+    ref = O.standard_attention(heads_of(qkv_q), heads_of(k), heads_of(v), mask)
+    ref = ref.permute(0, 2, 1, 3).reshape(b, sq, h)
+    kvc = kv.cuda()
+    out, lse = ops.attn_fwd(qkv_q.cuda(), kvc[..., :h], kvc[..., h:], heads, sep=sep, want_lse=True)
+    assert rel_err(out, ref) < 2e-2
+    scores = torch.matmul(heads_of(qkv_q) / 8.0, heads_of(k).transpose(-1, -2))
+    scores = scores * mask - 10000.0 * (1 - mask)
+    assert (lse.cpu() - torch.logsumexp(scores, dim=-1)).abs().max().item() < 2e-2
+
+
+def test_embedding_fwd_bwd(ops):
+    g = torch.Generator().manual_seed(5)
+    V, P, h, rows = 1000, 128, 256, 300
+    wte, wpe = bf(torch.randn((V, h), generator=g)), bf(torch.randn((P, h), generator=g))
+    ids, pos = torch.randint(0, V, (rows,), generator=g), torch.randint(0, P, (rows,), generator=g)
+    am = torch.zeros(1, device="cuda")
+    out = ops.embed_fwd(ids.cuda(), pos.cuda(), wte.cuda(), wpe.cuda(), am)
+    ref = wte.float()[ids] + wpe.float()[pos]
+    assert rel_err(out, ref) < 1e-6 and am.item() == ref.abs().max().item()
+    dx = torch.randn((rows, h), generator=g)
+    dwte, dwpe = torch.zeros((V, h), dtype=torch.bfloat16, device="cuda"), torch.zeros((P, h), dtype=torch.bfloat16,
+                                                                                       device="cuda")
+    ops.embed_bwd(ids.cuda(), pos.cuda(), dx.cuda(), dwte, dwpe)
+    r1 = torch.zeros((V, h)).index_add_(0, ids, dx)
+    r2 = torch.zeros((P, h)).index_add_(0, pos, dx)
+    assert rel_err(dwte, r1) < 2e-2 and rel_err(dwpe, r2) < 3e-2
+
+
+@pytest.mark.parametrize("rows,V", [(64, 58240), (33, 1003)])
+def test_cross_entropy_fwd_bwd(ops, rows, V):
+    g = torch.Generator().manual_seed(V)
+    ld = (V + 3) // 4 * 4
+    logits = torch.randn((rows, ld), generator=g) * 4
+    target = torch.randint(0, V, (rows,), generator=g)
+    lr = logits[:, :V].clone().requires_grad_(True)
+    ref = O.vocab_parallel_cross_entropy(lr, target)
+    lg = logits.cuda()[:, :V]
+    loss, rmax, rsum = ops.cross_entropy_fwd(lg, target.cuda())
+    assert (loss.cpu() - ref.detach()).abs().max().item() < 1e-4
+    gl = torch.rand(rows, generator=g)
+    ref.backward(gl)
+    dl = ops.cross_entropy_bwd(lg, target.cuda(), rmax, rsum, gl.cuda())
+    assert (dl.float().cpu() - lr.grad).abs().max().item() < 4e-3 * lr.grad.abs().max().item() + 1e-6
+
+
+def test_gelu_bwd_and_colsum(ops):
+    g = torch.Generator().manual_seed(9)
+    pre, dact = bf(torch.randn((128, 1024), generator=g) * 2), bf(torch.randn((128, 1024), generator=g))
+    pr = pre.float().requires_grad_(True)
+    O.gelu(pr).backward(dact.float())
+    assert rel_err(ops.gelu_bwd(pre.cuda(), dact.cuda()), pr.grad) < 1e-2
+    assert rel_err(ops.colsum(dact.cuda()), dact.float().sum(0)) < 1e-2
