@@ -35,6 +35,7 @@ def _declare(lib):
         "cv_layernorm_absmax_bwd": [P, I, P, I, P, P, P, P, P, I, P, P, P, I, I, P],
         "cv_absmax": [P, I, L, P, P],
         "cv_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, P],
+        "cv_attn_bwd": [P, L, L, P, L, L, P, L, L, P, P, P, P, P, I, I, I, I, I, P],
         "cv_embed_fwd": [P, P, P, P, P, P, I, I, P],
         "cv_embed_bwd": [P, P, P, P, P, I, I, P],
         "cv_cross_entropy_fwd": [P, L, P, P, P, P, I, I, P],
@@ -44,6 +45,8 @@ def _declare(lib):
     })
     lib.cv_layernorm_bwd_workspace_bytes.argtypes = [I, I]
     lib.cv_layernorm_bwd_workspace_bytes.restype = L
+    lib.cv_attn_bwd_workspace_bytes.argtypes = [I, I, I, I]
+    lib.cv_attn_bwd_workspace_bytes.restype = L
     lib.cv_colsum_workspace_bytes.argtypes = [I]
     lib.cv_colsum_workspace_bytes.restype = L
     for name, args in sigs.items():

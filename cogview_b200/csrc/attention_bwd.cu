@@ -1,0 +1,397 @@
+// cv_attn_bwd: backward of the fused dense attention (autograd of standard_attention,
+// /root/reference/mpu/sparse_transformer.py:652-673, which the reference gets from torch autograd over
+// materialised [b, np, s, s] tensors).  Recomputes P from Q, K and the saved log-sum-exp; nothing of
+// size [s, s] reaches HBM.
+//
+//   P = exp(S - lse),  S = scale * Q K^T (masked entries: -10000, gradient 0)
+//   dV = P^T dO        dP = dO V^T        dS = P o (dP - D),  D = rowsum(dO o O)
+//   dQ = scale * dS K  dK = scale * dS^T Q
+//
+// One CTA per (128-key block, head, batch) loops over the query blocks that can see it.  All five products
+// run on tcgen05 with TMEM accumulators; every operand is used in place from 128B-swizzled TMA tiles, in
+// K-major or MN-major form as the product needs (the same Q / dO / K tiles serve both):
+//   S^T  = K Q^T      (A = K   K-major, B = Q  K-major)   [keys x queries]
+//   dP^T = V dO^T     (A = V   K-major, B = dO K-major)
+//   dV  += P^T dO     (A = P^T K-major (smem, written by the softmax warps), B = dO MN-major)
+//   dK  += dS^T Q     (A = dS^T K-major (smem),                               B = Q  MN-major)
+//   dQ_i = dS K       (A = dS^T read MN-major,                                B = K  MN-major)
+// dV / dK stay in TMEM for the whole loop; dQ tiles are reduced into an fp32 buffer with vector red.add.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/cogview_b200.h"
+
+namespace {
+using namespace cv;
+
+constexpr int BLK = 128;
+constexpr int HD = 64;
+constexpr int TILE_BYTES = BLK * HD * 2;      // 16 KB: one [128 x 64] bf16 tile
+constexpr int PT_BYTES = BLK * BLK * 2;       // 32 KB: [128 keys x 128 queries] bf16
+constexpr int QDO_STAGES = 2;
+constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + QDO_STAGES * 2 * TILE_BYTES /*Q,dO*/ + 2 * PT_BYTES /*P^T,dS^T*/ +
+                           QDO_STAGES * 2 * BLK * 4 /*lse2, D*/ + 1024 + 256;
+constexpr int NUM_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct BwdParams {
+    int b, heads, s;
+    int sep_eff;
+    float scale, scale_log2;
+    const float* lse;    // [b, heads, s]
+    const float* delta;  // [b, heads, s]
+    float* dq_acc;       // [b, s, heads*HD] fp32, zero-initialised
+    __nv_bfloat16* dqkv; // [b, s, 3*heads*HD]
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + TILE_BYTES;
+    uint8_t* sQDO = sV + TILE_BYTES;                               // stage s: Q then dO
+    uint8_t* sPT = sQDO + QDO_STAGES * 2 * TILE_BYTES;
+    uint8_t* sDST = sPT + PT_BYTES;
+    float* sLse = reinterpret_cast<float*>(sDST + PT_BYTES);       // [stages][128]
+    float* sDelta = sLse + QDO_STAGES * BLK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + QDO_STAGES * BLK);
+    uint64_t* kv_full = bars;                  // 1
+    uint64_t* qdo_full = bars + 1;             // [2]
+    uint64_t* qdo_empty = qdo_full + QDO_STAGES;
+    uint64_t* sdp_full = qdo_empty + QDO_STAGES;   // 1: S^T and dP^T ready in TMEM
+    uint64_t* pds_full = sdp_full + 1;             // 1: P^T / dS^T written to smem (and S^T/dP^T TMEM consumed)
+    uint64_t* pds_free = pds_full + 1;             // 1: MMAs reading P^T / dS^T smem retired
+    uint64_t* dq_full = pds_free + 1;              // 1
+    uint64_t* dq_free = dq_full + 1;               // 1
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dq_free + 1);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+    const int k0 = kb * BLK;
+    const int nqb = (p.s + BLK - 1) / BLK;
+    const int i_start = (k0 < p.sep_eff) ? 0 : kb;   // first query block that sees any key of this block
+    const int ntiles = nqb - i_start;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < QDO_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+        mbar_init(sdp_full, 1);
+        mbar_init(pds_full, 128);
+        mbar_init(pds_free, 1);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_free, 128);
+        fence_barrier_init();
+    }
+    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    constexpr uint32_t TM_ST = 0, TM_DPT = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+            tma_load_3d(sK, &tmK, kv_full, head * HD, k0, batch);
+            tma_load_3d(sV, &tmV, kv_full, head * HD, k0, batch);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int q0 = (i_start + t) * BLK;
+                mbar_wait(&qdo_empty[stage], phase ^ 1);
+                uint8_t* sQ = sQDO + stage * 2 * TILE_BYTES;
+                mbar_expect_tx(&qdo_full[stage], 2 * TILE_BYTES);
+                tma_load_3d(sQ, &tmQ, &qdo_full[stage], head * HD, q0, batch);
+                tma_load_3d(sQ + TILE_BYTES, &tmDO, &qdo_full[stage], head * HD, q0, batch);
+                if (++stage == QDO_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(BLK, BLK, 0, 0);
+            constexpr uint32_t idesc_acc = make_idesc_bf16(BLK, HD, 0, 1);   // A K-major (smem P^T/dS^T), B MN-major
+            constexpr uint32_t idesc_dq = make_idesc_bf16(BLK, HD, 1, 1);    // A MN-major (dS^T read as dS), B MN-major
+            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+            auto issue_sdp = [&](int stage) {
+                const uint32_t q_addr = smem_u32(sQDO + stage * 2 * TILE_BYTES);
+                const uint32_t do_addr = q_addr + TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16(tmem_base + TM_ST, make_smem_desc_sw128(k_addr + k * 32, 0, 1024),
+                             make_smem_desc_sw128(q_addr + k * 32, 0, 1024), idesc_s, k != 0);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16(tmem_base + TM_DPT, make_smem_desc_sw128(v_addr + k * 32, 0, 1024),
+                             make_smem_desc_sw128(do_addr + k * 32, 0, 1024), idesc_s, k != 0);
+                umma_commit(sdp_full);
+            };
+            mbar_wait(kv_full, 0);
+            int stage = 0; uint32_t phase = 0;
+            mbar_wait(&qdo_full[0], 0);
+            tc_fence_after();
+            issue_sdp(0);
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(pds_full, t & 1);           // P^T / dS^T in smem; S^T / dP^T TMEM consumed
+                if (t > 0) mbar_wait(dq_free, (t - 1) & 1);   // previous dQ tile drained from TMEM
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(sQDO + stage * 2 * TILE_BYTES);
+                const uint32_t do_addr = q_addr + TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BLK / 16; ++k) {   // reduction over the 128 queries of this tile
+                    const uint32_t a_off = (k >> 2) * (BLK * 128) + (k & 3) * 32;
+                    umma_f16(tmem_base + TM_DV, make_smem_desc_sw128(pt_addr + a_off, 0, 1024),
+                             make_smem_desc_sw128(do_addr + k * 2048, BLK * 128, 1024), idesc_acc, (t | k) != 0);
+                    umma_f16(tmem_base + TM_DK, make_smem_desc_sw128(dst_addr + a_off, 0, 1024),
+                             make_smem_desc_sw128(q_addr + k * 2048, BLK * 128, 1024), idesc_acc, (t | k) != 0);
+                }
+#pragma unroll
+                for (int k = 0; k < BLK / 16; ++k)     // reduction over the 128 keys of this block
+                    umma_f16(tmem_base + TM_DQ, make_smem_desc_sw128(dst_addr + k * 2048, BLK * 128, 1024),
+                             make_smem_desc_sw128(k_addr + k * 2048, BLK * 128, 1024), idesc_dq, k != 0);
+                umma_commit(&qdo_empty[stage]);
+                umma_commit(pds_free);
+                umma_commit(dq_full);
+                if (++stage == QDO_STAGES) { stage = 0; phase ^= 1; }
+                if (t + 1 < ntiles) {
+                    mbar_wait(&qdo_full[stage], phase);
+                    tc_fence_after();
+                    issue_sdp(stage);
+                }
+            }
+        }
+    } else {
+        const int q = warp_idx & 3;
+        const int row = q * 32 + lane;             // key row within the block
+        const int kj = k0 + row;
+        const int epi_tid = threadIdx.x - 64;
+        const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+        const float masked_val = -10000.0f * LOG2E;
+        const size_t stat_base = ((size_t)batch * p.heads + head) * p.s;
+        int stage = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int q0 = (i_start + t) * BLK;
+            // stage lse (log2 domain) and delta of this query block
+            {
+                const int qi = q0 + epi_tid;
+                sLse[stage * BLK + epi_tid] = (qi < p.s) ? p.lse[stat_base + qi] * LOG2E : 0.f;
+                sDelta[stage * BLK + epi_tid] = (qi < p.s) ? p.delta[stat_base + qi] : 0.f;
+            }
+            named_bar_sync(1, 128);
+            mbar_wait(sdp_full, t & 1);
+            tc_fence_after();
+            if (t > 0) mbar_wait(pds_free, (t - 1) & 1);   // MMAs of the previous tile no longer read P^T / dS^T
+            const bool full_vis = (q0 + BLK <= p.s) && (k0 + BLK <= p.s) &&
+                                  ((k0 + BLK <= p.sep_eff) || (k0 + BLK - 1 <= q0));
+            const float* lse2 = sLse + stage * BLK;
+            const float* dlt = sDelta + stage * BLK;
+            uint8_t* prow = sPT + row * 128;
+            uint8_t* drow = sDST + row * 128;
+#pragma unroll 1
+            for (int c = 0; c < BLK / 32; ++c) {
+                uint32_t sr[32], dr[32];
+                tmem_ld_x32(lane_addr + TM_ST + c * 32, sr);
+                tmem_ld_x32(lane_addr + TM_DPT + c * 32, dr);
+                tmem_ld_wait();
+                float pv[32], dv[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int col = c * 32 + i;
+                    const int qi = q0 + col;
+                    float s2 = __uint_as_float(sr[i]) * p.scale_log2;
+                    float pr;
+                    if (full_vis) {
+                        pr = exp2f(s2 - lse2[col]);
+                    } else {
+                        const bool vis = (kj < p.sep_eff) || (kj <= qi);
+                        if (!vis) s2 = masked_val;
+                        pr = (kj < p.s && qi < p.s) ? exp2f(s2 - lse2[col]) : 0.f;
+                    }
+                    pv[i] = pr;
+                    dv[i] = pr * (__uint_as_float(dr[i]) - dlt[col]) * p.scale;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {          // 4 chunks of 8 queries (16 bytes)
+                    uint4 a, d;
+                    a.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]); a.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
+                    a.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]); a.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
+                    d.x = pack_bf16x2(dv[g * 8 + 0], dv[g * 8 + 1]); d.y = pack_bf16x2(dv[g * 8 + 2], dv[g * 8 + 3]);
+                    d.z = pack_bf16x2(dv[g * 8 + 4], dv[g * 8 + 5]); d.w = pack_bf16x2(dv[g * 8 + 6], dv[g * 8 + 7]);
+                    const int chunk = c * 4 + g;           // 16-byte chunk index along the 128 queries
+                    const int sub = chunk >> 3, cc = chunk & 7;
+                    const int off = sub * (BLK * 128) + ((cc ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(prow + off) = a;
+                    *reinterpret_cast<uint4*>(drow + off) = d;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(pds_full);
+            // dQ tile of this (query block, key block) pair
+            mbar_wait(dq_full, t & 1);
+            tc_fence_after();
+            {
+                uint32_t r[HD];
+                uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+                uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+                tmem_ld_x32(lane_addr + TM_DQ, r0);
+                tmem_ld_x32(lane_addr + TM_DQ + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(dq_free);
+                const int qi = q0 + row;               // here `row` indexes the query (dQ tile rows are queries)
+                if (qi < p.s) {
+                    float* dst = p.dq_acc + ((size_t)batch * p.s + qi) * (p.heads * HD) + head * HD;
+#pragma unroll
+                    for (int i = 0; i < HD; i += 4)
+                        red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                   __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                }
+            }
+            if (++stage == QDO_STAGES) stage = 0;
+        }
+        // dK / dV of this key block (complete once the last tile's MMAs retired: dq_full of the last tile)
+        if (ntiles > 0 && kj < p.s) {
+            const int H3 = 3 * p.heads * HD;
+            __nv_bfloat16* base = p.dqkv + ((size_t)batch * p.s + kj) * H3 + head * HD;
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                uint32_t r[HD];
+                uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+                uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+                const uint32_t col = which == 0 ? TM_DK : TM_DV;
+                tmem_ld_x32(lane_addr + col, r0);
+                tmem_ld_x32(lane_addr + col + 32, r1);
+                tmem_ld_wait();
+                __nv_bfloat16* dst = base + (which == 0 ? 1 : 2) * (p.heads * HD);
+#pragma unroll
+                for (int c = 0; c < HD / 8; ++c) {
+                    uint4 pk;
+                    pk.x = pack_bf16x2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
+                    pk.y = pack_bf16x2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
+                    pk.z = pack_bf16x2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
+                    pk.w = pack_bf16x2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
+                    *reinterpret_cast<uint4*>(dst + c * 8) = pk;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// delta[b, head, q] = sum_d dO[b, q, head, d] * O[b, q, head, d]
+__global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                      float* __restrict__ delta, int b, int heads, int s) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (batch, q, head), head fastest
+    if (idx >= b * s * heads) return;
+    const int head = idx % heads;
+    const int tok = idx / heads;
+    const uint4* po = reinterpret_cast<const uint4*>(o + (size_t)tok * heads * HD + head * HD);
+    const uint4* pd = reinterpret_cast<const uint4*>(d_o + (size_t)tok * heads * HD + head * HD);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+        uint4 a = po[i], c = pd[i];
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            acc += __low2float(pa[t]) * __low2float(pc[t]) + __high2float(pa[t]) * __high2float(pc[t]);
+    }
+    const int bi = tok / s, qi = tok % s;
+    delta[((size_t)bi * heads + head) * s + qi] = acc;
+}
+
+// dqkv[:, 0:h] = bf16(dq_acc)
+__global__ void attn_bwd_dq_store_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv, size_t rows,
+                                         int h) {
+    const size_t n4 = rows * (size_t)(h / 4);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (h / 4);
+        const int c = (int)(i % (h / 4)) * 4;
+        float4 v = *reinterpret_cast<const float4*>(dq + r * h + c);
+        uint2 u;
+        u.x = pack_bf16x2(v.x, v.y);
+        u.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dqkv + r * 3 * h + c) = u;
+    }
+}
+
+int encode_map3(CUtensorMap* m, const void* base, int b, int s, int cols, int64_t ld, int64_t bs) {
+    uint64_t dims[3] = {(uint64_t)cols, (uint64_t)s, (uint64_t)b};
+    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)bs * 2};
+    uint32_t box[3] = {64, BLK, 1};
+    return cvh::encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, str, box, nullptr, cvh::Swizzle::B128);
+}
+
+}  // namespace
+
+extern "C" int64_t cv_attn_bwd_workspace_bytes(int b, int heads, int head_dim, int s) {
+    return (int64_t)b * s * heads * head_dim * 4 /*dq fp32*/ + (int64_t)b * heads * s * 4 /*delta*/;
+}
+
+extern "C" int cv_attn_bwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                           const void* v, int64_t ldv, int64_t bsv, const void* out, const void* d_out,
+                           const float* lse, void* dqkv, void* workspace, int b, int heads, int head_dim, int s,
+                           int sep, void* stream) {
+    CV_REQUIRE(q && k && v && out && d_out && lse && dqkv && workspace, "null pointer");
+    CV_REQUIRE(head_dim == HD, "head_dim must be 64");
+    CV_REQUIRE(b > 0 && heads > 0 && s > 0 && sep >= 0 && sep <= s, "bad sizes");
+    CV_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0,
+               "strides must be multiples of 8 elements");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int h = heads * HD;
+    float* dq_acc = static_cast<float*>(workspace);
+    float* delta = dq_acc + (size_t)b * s * h;
+    CV_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)b * s * h * sizeof(float), st));
+    {
+        const int n = b * s * heads;
+        attn_bwd_delta_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
+                                                              static_cast<const __nv_bfloat16*>(d_out), delta, b,
+                                                              heads, s);
+        CV_LAUNCH_CHECK();
+    }
+    alignas(64) CUtensorMap tmQ, tmK, tmV, tmDO;
+    int rc;
+    if ((rc = encode_map3(&tmQ, q, b, s, h, ldq, bsq))) return rc;
+    if ((rc = encode_map3(&tmK, k, b, s, h, ldk, bsk))) return rc;
+    if ((rc = encode_map3(&tmV, v, b, s, h, ldv, bsv))) return rc;
+    if ((rc = encode_map3(&tmDO, d_out, b, s, h, h, (int64_t)s * h))) return rc;
+    BwdParams p;
+    p.b = b; p.heads = heads; p.s = s;
+    p.sep_eff = sep;
+    p.scale = 1.0f / sqrtf((float)head_dim);
+    p.scale_log2 = p.scale * LOG2E;
+    p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
+    p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid((s + BLK - 1) / BLK, heads, b);
+    attn_bwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, tmDO, p);
+    CV_LAUNCH_CHECK();
+    {
+        const size_t rows = (size_t)b * s;
+        const size_t n4 = rows * (h / 4);
+        size_t blocks = (n4 + 255) / 256;
+        size_t cap = (size_t)cvh::num_sms() * 8;
+        attn_bwd_dq_store_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+            dq_acc, static_cast<__nv_bfloat16*>(dqkv), rows, h);
+        CV_LAUNCH_CHECK();
+    }
+    return 0;
+}

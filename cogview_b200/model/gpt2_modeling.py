@@ -1,0 +1,114 @@
+"""GPT-2 model — mirror of the reference's model/gpt2_modeling.py (GPT2Model :55-123,
+gpt2_get_params_for_weight_decay_optimization :35-52): same constructor and forward signatures, same
+state_dict keys (`word_embeddings.weight`, `transformer.*`)."""
+import torch
+
+from .. import mpu, ops
+from ..mpu.layers import _as_bf16
+from ..mpu.sparse_transformer import _EmbedFn, mask_to_sep
+
+
+def init_method_normal(std=0.02):
+    def init_(tensor):
+        return torch.nn.init.normal_(tensor, mean=0.0, std=std)
+    return init_
+
+
+def gpt2_get_params_for_weight_decay_optimization(module):
+    """Weights decay; biases and LayerNorm parameters do not (model/gpt2_modeling.py:35-52)."""
+    weight_decay_params = {'params': []}
+    no_weight_decay_params = {'params': [], 'weight_decay': 0.0}
+    for module_ in module.modules():
+        if isinstance(module_, (mpu.LayerNorm, torch.nn.LayerNorm)):
+            no_weight_decay_params['params'].extend([p for p in list(module_._parameters.values()) if p is not None])
+        else:
+            weight_decay_params['params'].extend(
+                [p for n, p in list(module_._parameters.items()) if p is not None and n != 'bias'])
+            no_weight_decay_params['params'].extend(
+                [p for n, p in list(module_._parameters.items()) if p is not None and n == 'bias'])
+    return weight_decay_params, no_weight_decay_params
+
+
+class _LogitsFn(torch.autograd.Function):
+    """logits = h W^T with the tied word-embedding matrix (model/gpt2_modeling.py:117-118), fp32 output."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight):
+        w = _as_bf16(weight)
+        ctx.save_for_backward(hidden, w)
+        ctx.wdtype = weight.dtype
+        V = w.shape[0]
+        ld = (V + 3) // 4 * 4
+        out = torch.empty((hidden.shape[0], ld), dtype=torch.float32, device=hidden.device)
+        ops.gemm(hidden, w, out_dtype=torch.float32, out=out[:, :V] if ld != V else out)
+        return out[:, :V]
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        hidden, w = ctx.saved_tensors
+        dl = _as_bf16(d_logits)
+        if dl.stride(1) != 1 or dl.stride(0) % 8 != 0:
+            V = dl.shape[1]
+            buf = torch.empty((dl.shape[0], (V + 7) // 8 * 8), dtype=torch.bfloat16, device=dl.device)
+            buf[:, :V].copy_(dl)
+            dl = buf[:, :V]
+        d_hidden = ops.gemm(dl, w, b_mn_major=True)
+        d_w = ops.gemm(dl, hidden, a_mn_major=True, b_mn_major=True)
+        return d_hidden, d_w.to(ctx.wdtype)
+
+
+class GPT2Model(torch.nn.Module):
+    """GPT-2 language model over concatenated text + image tokens.  forward returns (logits, *mems)."""
+
+    def __init__(self, num_layers, vocab_size, hidden_size, num_attention_heads, embedding_dropout_prob,
+                 attention_dropout_prob, output_dropout_prob, max_sequence_length, max_memory_length,
+                 checkpoint_activations, checkpoint_num_layers=1, parallel_output=True, query_window=128,
+                 key_window_times=6, num_pivot=768):
+        super().__init__()
+        self.parallel_output = parallel_output
+        init_method = init_method_normal(std=0.02)
+        self.word_embeddings = mpu.VocabParallelEmbedding(vocab_size, hidden_size, init_method=init_method)
+        self.transformer = mpu.GPT2ParallelTransformer(
+            num_layers, hidden_size, num_attention_heads, max_sequence_length, max_memory_length,
+            embedding_dropout_prob, attention_dropout_prob, output_dropout_prob, checkpoint_activations,
+            checkpoint_num_layers, query_window=query_window, key_window_times=key_window_times, num_pivot=num_pivot)
+
+    def forward(self, input_ids, position_ids, attention_mask, txt_indices_bool, img_indices_bool, is_sparse, *mems,
+                logits_last_only=False):
+        """Same positional arguments as the reference (model/gpt2_modeling.py:106).  Returns
+        (logits [b, s, V] fp32, *mems).  `logits_last_only` (keyword, extension): only the last position's
+        logits are computed — what the sampling loop reads (generation/sampling.py:155)."""
+        if is_sparse != 0:
+            raise NotImplementedError('sparse attention (is_sparse=%d) is not implemented in this round' % is_sparse)
+        tr = self.transformer
+        if tr.training and tr.embedding_dropout_prob > 0:
+            raise NotImplementedError('embedding dropout > 0 is not supported yet')
+        b, sq = input_ids.shape
+        mem_len = mems[0].size(1) if mems else 0
+        sep = mask_to_sep(attention_mask, sq, sq + mem_len)
+        if position_ids.shape != input_ids.shape:
+            position_ids = position_ids.expand_as(input_ids)
+        wte, wpe = self.word_embeddings.weight, tr.position_embeddings.weight
+        if torch.is_grad_enabled() and (wte.requires_grad or wpe.requires_grad):
+            x, am_x = _EmbedFn.apply(input_ids, position_ids, wte, wpe)
+        else:
+            am_x = ops.new_scalars(1, wte.device)
+            x = ops.embed_fwd(input_ids, position_ids, _as_bf16(wte.detach()).contiguous(),
+                              _as_bf16(wpe.detach()).contiguous(), am_x)
+        y, mem_layers = tr.run_layers(x, am_x, b, sq, sep, mems)
+        h = y.shape[1]
+        if logits_last_only:
+            y = y.view(b, sq, h)[:, -1].contiguous()
+            sq_out = 1
+        else:
+            sq_out = sq
+        if torch.is_grad_enabled() and (y.requires_grad or wte.requires_grad):
+            logits = _LogitsFn.apply(y, wte)
+        else:
+            logits = _LogitsFn.forward(_NoCtx(), y, wte.detach())
+        return (logits.view(b, sq_out, -1), *mem_layers)
+
+
+class _NoCtx:
+    def save_for_backward(self, *a):
+        pass

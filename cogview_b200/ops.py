@@ -123,6 +123,21 @@ def attn_fwd(q, k, v, heads, *, sep=0, want_lse=False):
     return (out, lse) if want_lse else out
 
 
+def attn_bwd(q, k, v, out, d_out, lse, heads, *, sep=0):
+    """Backward of attn_fwd for sq == sk.  Returns dqkv [b, s, 3*heads*64] bf16 (dQ | dK | dV)."""
+    require_cuda(q, k, v, out, d_out, lse)
+    b, s, h = q.shape
+    assert k.shape[1] == s, "attention backward needs sq == sk"
+    assert out.is_contiguous() and d_out.is_contiguous() and d_out.dtype == torch.bfloat16
+    dqkv = torch.empty((b, s, 3 * h), dtype=torch.bfloat16, device=q.device)
+    ws = torch.empty(lib().cv_attn_bwd_workspace_bytes(b, heads, 64, s) // 4, dtype=torch.float32, device=q.device)
+    rc = lib().cv_attn_bwd(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
+                           v.stride(0), ptr(out), ptr(d_out), ptr(lse), ptr(dqkv), ptr(ws), b, heads, 64, s, int(sep),
+                           stream_ptr())
+    check(rc, "cv_attn_bwd")
+    return dqkv
+
+
 # ----------------------------------------------------------------------------------------------------
 # embedding, cross-entropy, small backward helpers
 # ----------------------------------------------------------------------------------------------------

@@ -79,6 +79,14 @@ int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t 
                 int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, float* lse, int b, int heads,
                 int head_dim, int sq, int sk, int sep, void* stream);
 
+/* Backward of cv_attn_fwd for sq == sk (training).  q/k/v as in cv_attn_fwd; out, d_out: [b, s, heads*64] bf16
+ * contiguous; lse from the forward.  dqkv: [b, s, 3*heads*64] bf16 (dQ | dK | dV, the layout of the packed QKV
+ * GEMM output, so the QKV dgrad/wgrad GEMMs read it directly).  workspace: cv_attn_bwd_workspace_bytes(). */
+int64_t cv_attn_bwd_workspace_bytes(int b, int heads, int head_dim, int s);
+int cv_attn_bwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
+                int64_t ldv, int64_t bsv, const void* out, const void* d_out, const float* lse, void* dqkv,
+                void* workspace, int b, int heads, int head_dim, int s, int sep, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Embedding: hidden = wte[ids] + wpe[pos] (fp32) and max|hidden|
  *   replaces VocabParallelEmbedding.forward (mpu/layers.py:117-133) + position add (mpu/sparse_transformer.py:522-523)

@@ -157,3 +157,27 @@ def test_gelu_bwd_and_colsum(ops):
     O.gelu(pr).backward(dact.float())
     assert rel_err(ops.gelu_bwd(pre.cuda(), dact.cuda()), pr.grad) < 1e-2
     assert rel_err(ops.colsum(dact.cuda()), dact.float().sum(0)) < 1e-2
+
+
+@pytest.mark.parametrize("b,heads,s,sep", [(2, 2, 128, 0), (1, 3, 200, 0), (2, 2, 384, 0), (1, 2, 300, 130),
+                                           (1, 2, 1088, 0)])
+def test_attention_bwd_matches_autograd_of_standard_attention(ops, b, heads, s, sep):
+    g = torch.Generator().manual_seed(s + sep)
+    h = heads * 64
+    qkv = bf(torch.randn((b, s, 3 * h), generator=g))
+    d_out = bf(torch.randn((b, s, h), generator=g))
+
+    def heads_of(t):
+        return t.view(b, s, heads, 64).permute(0, 2, 1, 3)
+
+    qr, kr, vr = (qkv[..., i * h:(i + 1) * h].float().clone().requires_grad_(True) for i in range(3))
+    ref = O.standard_attention(heads_of(qr), heads_of(kr), heads_of(vr), O.build_sep_mask(s, s, sep))
+    ref = ref.permute(0, 2, 1, 3).reshape(b, s, h)
+    ref.backward(d_out.float())
+    qc = qkv.cuda()
+    out, lse = ops.attn_fwd(qc[..., :h], qc[..., h:2 * h], qc[..., 2 * h:], heads, sep=sep, want_lse=True)
+    dqkv = ops.attn_bwd(qc[..., :h], qc[..., h:2 * h], qc[..., 2 * h:], out, d_out.cuda(), lse, heads, sep=sep)
+    for name, got, want in (("dq", dqkv[..., :h], qr.grad), ("dk", dqkv[..., h:2 * h], kr.grad),
+                            ("dv", dqkv[..., 2 * h:], vr.grad)):
+        e = rel_err(got, want)
+        assert e < 3e-2, (name, e)
