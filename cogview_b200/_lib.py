@@ -36,6 +36,8 @@ def _declare(lib):
         "cv_absmax": [P, I, L, P, P],
         "cv_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, P],
         "cv_attn_bwd": [P, L, L, P, L, L, P, L, L, P, P, P, P, P, I, I, I, I, I, P],
+        "cv_linear_small_m": [P, L, P, L, P, P, L, I, I, P, I, I, I, P],
+        "cv_attn_decode": [P, P, L, P, I, P, P, I, I, I, I, I, P],
         "cv_embed_fwd": [P, P, P, P, P, P, I, I, P],
         "cv_embed_bwd": [P, P, P, P, P, I, I, P],
         "cv_cross_entropy_fwd": [P, L, P, P, P, P, I, I, P],
@@ -47,6 +49,8 @@ def _declare(lib):
     lib.cv_layernorm_bwd_workspace_bytes.restype = L
     lib.cv_attn_bwd_workspace_bytes.argtypes = [I, I, I, I]
     lib.cv_attn_bwd_workspace_bytes.restype = L
+    lib.cv_attn_decode_workspace_bytes.argtypes = [I, I, I]
+    lib.cv_attn_decode_workspace_bytes.restype = L
     lib.cv_colsum_workspace_bytes.argtypes = [I]
     lib.cv_colsum_workspace_bytes.restype = L
     for name, args in sigs.items():

@@ -257,9 +257,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (++stage == QDO_STAGES) stage = 0;
         }
         // dK / dV of this key block (complete once the last tile's MMAs retired: dq_full of the last tile)
-        if (ntiles > 0 && kj < p.s) {
+        // (tcgen05.ld is warp-collective: every lane loads, only in-range rows store)
+        {
             const int H3 = 3 * p.heads * HD;
-            __nv_bfloat16* base = p.dqkv + ((size_t)batch * p.s + kj) * H3 + head * HD;
+            const bool row_ok = kj < p.s;
+            __nv_bfloat16* base = p.dqkv + ((size_t)batch * p.s + (row_ok ? kj : 0)) * H3 + head * HD;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
                 uint32_t r[HD];
@@ -270,6 +272,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tmem_ld_x32(lane_addr + col + 32, r1);
                 tmem_ld_wait();
                 __nv_bfloat16* dst = base + (which == 0 ? 1 : 2) * (p.heads * HD);
+                if (row_ok) {
 #pragma unroll
                 for (int c = 0; c < HD / 8; ++c) {
                     uint4 pk;
@@ -278,6 +281,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     pk.z = pack_bf16x2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
                     pk.w = pack_bf16x2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
                     *reinterpret_cast<uint4*>(dst + c * 8) = pk;
+                }
                 }
             }
         }

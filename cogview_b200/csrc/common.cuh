@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace cv {
 
@@ -80,15 +81,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Spin on the phase parity.  A bounded spin turns a protocol bug into a trap (an error the host
-// sees) instead of a hung GPU.
-#ifndef CV_SPIN_LIMIT
-#define CV_SPIN_LIMIT (1u << 24)
+// Spin on the phase parity.  A bounded wait (wall-clock, %globaltimer) turns a protocol bug into a trap
+// (an error the host sees) instead of a hung GPU.
+#ifndef CV_WAIT_TIMEOUT_NS
+#define CV_WAIT_TIMEOUT_NS 4000000000ull
 #endif
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (true) {
         asm volatile(
             "{\n\t"
@@ -100,7 +107,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (++spins > CV_SPIN_LIMIT) __trap();
+        if ((++spins & 0x3ff) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > CV_WAIT_TIMEOUT_NS) {
+                printf("cogview_b200: mbarrier wait timed out (block %d,%d,%d thread %d, smem 0x%x, parity %u)\n",
+                       blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, addr, parity);
+                __trap();
+            }
+        }
     }
 }
 

@@ -1,6 +1,8 @@
 """GPT-2 model — mirror of the reference's model/gpt2_modeling.py (GPT2Model :55-123,
 gpt2_get_params_for_weight_decay_optimization :35-52): same constructor and forward signatures, same
 state_dict keys (`word_embeddings.weight`, `transformer.*`)."""
+import os
+
 import torch
 
 from .. import mpu, ops
@@ -88,6 +90,9 @@ class GPT2Model(torch.nn.Module):
         sep = mask_to_sep(attention_mask, sq, sq + mem_len)
         if position_ids.shape != input_ids.shape:
             position_ids = position_ids.expand_as(input_ids)
+        fast = self._fast_decode(input_ids, position_ids, mems, b, sq)
+        if fast is not None:
+            return fast
         wte, wpe = self.word_embeddings.weight, tr.position_embeddings.weight
         if torch.is_grad_enabled() and (wte.requires_grad or wpe.requires_grad):
             x, am_x = _EmbedFn.apply(input_ids, position_ids, wte, wpe)
@@ -107,6 +112,27 @@ class GPT2Model(torch.nn.Module):
         else:
             logits = _LogitsFn.forward(_NoCtx(), y, wte.detach())
         return (logits.view(b, sq_out, -1), *mem_layers)
+
+
+def _fast_decode_impl(self, input_ids, position_ids, mems, b, sq):
+    """One token per sequence on the K|V cache (the call pattern of generation/sampling.py:147-151): CUDA-graph
+    replay of the weight-streaming decode step.  Returns None when the call does not qualify."""
+    tr = self.transformer
+    if (sq != 1 or not mems or tr.mems_mode != 'kv' or tr.max_memory_length <= 0 or torch.is_grad_enabled()
+            or b > 16 or os.environ.get('COGVIEW_B200_FAST_DECODE', '1') == '0'):
+        return None
+    from ..mpu import kv_cache
+    from ..mpu.decode import DecodeRunner
+    caches = kv_cache.prepare(tr, mems, b, sq)
+    runner = getattr(caches, 'runner', None)
+    if runner is None:
+        runner = caches.runner = DecodeRunner(self, caches,
+                                              use_graph=os.environ.get('COGVIEW_B200_CUDA_GRAPH', '1') != '0')
+    logits = runner.step(input_ids, position_ids, caches.t)
+    return (logits.view(b, 1, -1), *caches.views())
+
+
+GPT2Model._fast_decode = _fast_decode_impl
 
 
 class _NoCtx:

@@ -1,0 +1,89 @@
+"""Single-token decode step on the K|V cache, captured once as a CUDA graph and replayed per token.
+
+This is the fast path behind GPT2Model.forward when it is called the way generation/sampling.py:147-151 calls
+it (one new token per sequence, `mems` returned by the previous call, mems_mode 'kv').  Per layer:
+abs-max LN -> QKV linear -> cached attention (+ append) -> out-proj (+abs-max) -> LN + residual -> LN ->
+h->4h (+GELU) -> 4h->h (+abs-max) -> LN + residual, all weight-streaming kernels (cv_linear_small_m,
+cv_attn_decode) with the position read from device memory so the graph is replayable."""
+import torch
+
+from .. import ops
+from .layers import _as_bf16
+
+
+class DecodeRunner:
+    def __init__(self, model, caches, use_graph=True):
+        tr = model.transformer
+        self.model = model
+        self.caches = caches
+        self.b = caches.b
+        self.heads = tr.num_attention_heads
+        self.h = tr.hidden_size
+        dev = caches.buf.device
+        self.ids = torch.zeros((self.b, 1), dtype=torch.int64, device=dev)
+        self.pos = torch.zeros((self.b, 1), dtype=torch.int64, device=dev)
+        self.cur_len = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.logits = None
+        self.graph = None
+        self.use_graph = use_graph
+        # enough (batch, head, split) CTAs to cover the SMs
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.nsplit = max(1, min(16, -(-sms // (self.b * self.heads))))
+        self.params = None
+
+    def _gather_params(self):
+        tr = self.model.transformer
+        self.params = [tuple(_as_bf16(p.detach()) for p in layer.param_list()) for layer in tr.layers]
+        self.wte = _as_bf16(self.model.word_embeddings.weight.detach()).contiguous()
+        self.wpe = _as_bf16(tr.position_embeddings.weight.detach()).contiguous()
+        self.fl = (_as_bf16(tr.final_layernorm.weight.detach()), _as_bf16(tr.final_layernorm.bias.detach()),
+                   tr.final_layernorm.eps)
+        self.eps = tr.layers[0].layernorm_epsilon
+
+    def _run(self):
+        b, h, heads = self.b, self.h, self.heads
+        L = len(self.params)
+        scal = ops.new_scalars(4 * L + 1, self.ids.device)
+        x = ops.embed_fwd(self.ids, self.pos, self.wte, self.wpe, scal[4 * L:4 * L + 1])
+        am = scal[4 * L:4 * L + 1]
+        for i, P in enumerate(self.params):
+            (g1, b1, wqkv, bqkv, wd, bd, g3, b3, g2, b2, w1, bb1, w2, bb2, g4, b4) = P
+            s = scal[4 * i:4 * i + 4]
+            ln1, _, _ = ops.layernorm_absmax_fwd(x, am, g1, b1, self.eps)
+            qkv = ops.linear_small_m(ln1, wqkv, bqkv)
+            ctx = ops.attn_decode(qkv, self.caches.buf[i], heads, cur_len_dev=self.cur_len, nsplit=self.nsplit)
+            attn_out = ops.linear_small_m(ctx, wd, bd, absmax=s[0:1])
+            y, _, _ = ops.layernorm_absmax_fwd(attn_out, s[0:1], g3, b3, self.eps, residual=x,
+                                               out_dtype=torch.float32, absmax_out=s[1:2])
+            ln2, _, _ = ops.layernorm_absmax_fwd(y, s[1:2], g2, b2, self.eps)
+            h4 = ops.linear_small_m(ln2, w1, bb1, act=ops.ACT_GELU)
+            mlp_out = ops.linear_small_m(h4, w2, bb2, absmax=s[2:3])
+            x, _, _ = ops.layernorm_absmax_fwd(mlp_out, s[2:3], g4, b4, self.eps, residual=y,
+                                               out_dtype=torch.float32, absmax_out=s[3:4])
+            am = s[3:4]
+        yf, _, _ = ops.layernorm_absmax_fwd(x, am, self.fl[0], self.fl[1], self.fl[2])
+        self.logits = ops.linear_small_m(yf, self.wte, out_dtype=torch.float32)
+
+    def step(self, ids, pos, t):
+        """ids, pos: [b, 1] int64; t: tokens already cached.  Returns logits [b, V] fp32 (a static buffer)."""
+        if self.params is None:
+            self._gather_params()
+        self.ids.copy_(ids)
+        self.pos.copy_(pos)
+        self.cur_len.fill_(t)
+        if not self.use_graph:
+            self._run()
+        elif self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._run()
+                self._run()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._run()
+            self.graph.replay()
+        else:
+            self.graph.replay()
+        return self.logits

@@ -208,3 +208,39 @@ def colsum(dy):
     ws = torch.empty(lib().cv_colsum_workspace_bytes(cols) // 4, dtype=torch.float32, device=dy.device)
     check(lib().cv_colsum_bf16(ptr(dy), dy.stride(0), ptr(out), ptr(ws), rows, cols, stream_ptr()), "cv_colsum_bf16")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# decode (weight-streaming) kernels
+# ----------------------------------------------------------------------------------------------------
+def linear_small_m(x, w, bias=None, *, act=ACT_NONE, out_dtype=torch.bfloat16, absmax=None, out=None):
+    """y = x @ w^T + bias for 1 <= M <= 16 rows (x: [M,K] bf16, w: [N,K] bf16)."""
+    require_cuda(x, w, bias, absmax)
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    rc = lib().cv_linear_small_m(ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0),
+                                 int(out.dtype == torch.float32), int(act), ptr(absmax), M, N, K, stream_ptr())
+    check(rc, "cv_linear_small_m")
+    return out
+
+
+def attn_decode(qkv, cache, heads, *, cur_len=None, cur_len_dev=None, nsplit=1, out=None, workspace=None):
+    """qkv: [b, 3h] bf16; cache: [b, max_len, 2h] bf16 (K|V); appends the new token at cur_len and returns
+    the attention context [b, h] bf16."""
+    require_cuda(qkv, cache)
+    b, h3 = qkv.shape
+    h = h3 // 3
+    assert qkv.is_contiguous() and cache.stride(2) == 1 and cache.stride(1) == 2 * h and cache.shape[2] == 2 * h
+    if out is None:
+        out = torch.empty((b, h), dtype=torch.bfloat16, device=qkv.device)
+    if nsplit > 1 and workspace is None:
+        workspace = torch.empty(lib().cv_attn_decode_workspace_bytes(b, heads, nsplit) // 4, dtype=torch.float32,
+                                device=qkv.device)
+    rc = lib().cv_attn_decode(ptr(qkv), ptr(cache), cache.stride(0), ptr(cur_len_dev),
+                              -1 if cur_len is None else int(cur_len), ptr(out), ptr(workspace), b, heads, 64,
+                              cache.shape[1], nsplit, stream_ptr())
+    check(rc, "cv_attn_decode")
+    return out

@@ -112,6 +112,23 @@ int cv_gelu_bwd(const void* pre, const void* dact, void* dpre, int64_t n, void* 
 int64_t cv_colsum_workspace_bytes(int cols);
 int cv_colsum_bf16(const void* dy, int64_t ld, void* out, float* workspace, int rows, int cols, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Decode (one new token per sequence): HBM-bound weight streaming, CUDA cores.
+ *   cv_linear_small_m: y[M,N] = x[M,K] W[N,K]^T + bias (+GELU) (+abs-max), 1 <= M <= 16 — F.linear of
+ *     mpu/layers.py:243,319 and the last-token logits GEMM (model/gpt2_modeling.py:117) inside the sampling
+ *     loop (generation/sampling.py:147-155).  out bf16 or fp32.
+ *   cv_attn_decode: standard_attention (mpu/sparse_transformer.py:652-673) for sq = 1 over a K|V cache
+ *     [b, max_len, 2*heads*64]; qkv [b, 3*heads*64] holds q | k_new | v_new of the token at position cur_len,
+ *     which is appended to the cache by the same kernel.  cur_len comes from *cur_len_dev when non-NULL
+ *     (so a captured CUDA graph can be replayed), else from cur_len.  out [b, heads*64] bf16.
+ * ---------------------------------------------------------------------------------------------- */
+int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out,
+                      int64_t ldo, int out_is_f32, int act, float* absmax, int M, int N, int K, void* stream);
+int64_t cv_attn_decode_workspace_bytes(int b, int heads, int nsplit);
+int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_stride, const int* cur_len_dev, int cur_len,
+                   void* out, float* workspace, int b, int heads, int head_dim, int max_len, int nsplit,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
