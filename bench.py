@@ -1,0 +1,525 @@
+#!/usr/bin/env python
+"""bench.py — CogView-base 4B hot path on B200 (BASELINE.json metric: tokens/sec, train + AR sample).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sample|train|both]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Headline line (`value`, `e2e`): BASELINE.json configs[1] — 4B (48 L, d=2560, 40 heads, V=58240), 1089-token
+sequences, bf16, autoregressive sampling through the reference-facing API (generation.sampling.filling_sequence
+over GPT2Model): one step = prefill a 65-token context and generate 1024 image tokens for a batch of 4 beams
+(scripts/text2image.sh defaults).  The same JSON line carries a `train` object for configs[2] (one optimizer
+step on 4 x 1088 tokens per GPU: forward, vocab cross-entropy, backward, DP gradient all-reduce, fused AdamW).
+Synthetic tokens, random-init weights (no network for checkpoints).  `--impl reference` times the oracle port
+of the reference's CPU path (hidden-state `mems` semantics) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MODEL_4B = dict(num_layers=48, vocab_size=58240, hidden_size=2560, num_attention_heads=40, max_sequence_length=1089)
+MODEL_TINY = dict(num_layers=2, vocab_size=58240, hidden_size=256, num_attention_heads=4, max_sequence_length=1089)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="both", choices=["sample", "train", "both"])
+    ap.add_argument("--batch", type=int, default=4, help="beams per GPU (sampling) / sequences per GPU (training)")
+    ap.add_argument("--gen-tokens", type=int, default=1024)
+    ap.add_argument("--model", default="4b", choices=["4b", "tiny"])
+    ap.add_argument("--train-steps", type=int, default=None)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# model / workload construction
+# ----------------------------------------------------------------------------------------------------
+def build_model(cfg, max_memory_length, device):
+    from cogview_b200.model import GPT2Model
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(device):
+            model = GPT2Model(num_layers=cfg["num_layers"], vocab_size=cfg["vocab_size"],
+                              hidden_size=cfg["hidden_size"], num_attention_heads=cfg["num_attention_heads"],
+                              embedding_dropout_prob=0.0, attention_dropout_prob=0.0, output_dropout_prob=0.0,
+                              max_sequence_length=cfg["max_sequence_length"], max_memory_length=max_memory_length,
+                              checkpoint_activations=False)
+    finally:
+        torch.set_default_dtype(old)
+    return model
+
+
+class SampleArgs:
+    temperature = 1.0
+    top_k = 200
+    top_p = 0.0
+    is_sparse = 0
+    img_tokenizer_num_tokens = 8192
+
+
+def make_template(nb, gen_tokens, seed):
+    """'[ROI1] text [BASE] [BOI1] [MASK]*N' (generate_samples.py:204) as token ids; -nb marks generated slots."""
+    from cogview_b200.generation import sampling
+    tok = sampling.get_tokenizer(SampleArgs)
+    g = torch.Generator().manual_seed(seed)
+    text = torch.randint(8192, 58192, (62,), generator=g).tolist()
+    seq = [tok['[ROI1]']] + text + [tok['[BASE]'], tok['[BOI1]']] + [-1] * gen_tokens
+    sampling.add_interlacing_beam_marks(seq, nb=nb)
+    return torch.tensor(seq, dtype=torch.long)
+
+
+def param_count(model):
+    return sum(p.numel() for p in model.parameters())
+
+
+# ----------------------------------------------------------------------------------------------------
+# timing helpers
+# ----------------------------------------------------------------------------------------------------
+def dist_ready():
+    return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+
+def barrier():
+    if dist_ready():
+        torch.distributed.barrier()
+
+
+def timed(fn, steps, warmup, device_index):
+    """W untimed + K timed steps: barrier + sync on both sides, CUDA events on the launching stream, MAX over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(device_index)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if dist_ready():
+        t = torch.tensor([ms], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    return ms, clocks
+
+
+def launches():
+    from cogview_b200 import _lib
+    return int(_lib.lib().cv_launch_count())
+
+
+# ----------------------------------------------------------------------------------------------------
+# sampling workload (configs[1])
+# ----------------------------------------------------------------------------------------------------
+def run_sample(args, cfg, world, rank, dev_index):
+    from cogview_b200.generation import sampling
+    model = build_model(cfg, cfg["max_sequence_length"], "cuda").eval()
+    nb = args.batch
+    tmpl_host = make_template(nb, args.gen_tokens, seed=rank).pin_memory()
+    tmpl_dev = tmpl_host.cuda()
+    out_host = torch.empty((nb, tmpl_host.numel()), dtype=torch.long).pin_memory()
+    holder = {}
+
+    def step_dev():
+        with torch.no_grad():
+            holder["out"] = sampling.filling_sequence(model, tmpl_dev, SampleArgs)
+
+    def step_e2e():
+        with torch.no_grad():
+            seq = tmpl_host.cuda(non_blocking=True)
+            out = sampling.filling_sequence(model, seq, SampleArgs)
+            out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    tokens_per_step = nb * args.gen_tokens * world
+    l0 = launches()
+    ms_dev, clocks = timed(step_dev, args.steps, args.warmup, dev_index)
+    graph_nodes = 0
+    kv = model.transformer._kv
+    if kv is not None and getattr(kv, "runner", None) is not None:
+        graph_nodes = kv.runner.graph_launches * kv.runner.replays
+    n_launch = launches() - l0 + graph_nodes
+    ms_e2e, _ = timed(step_e2e, args.steps, 1, dev_index)
+    assert holder["out"].shape == (nb, tmpl_host.numel()) and int(holder["out"].min()) >= 0
+    assert int(holder["out"][:, -args.gen_tokens:].max()) < 8192, "generated tokens must be image codes"
+    res = dict(value=tokens_per_step * args.steps / (ms_dev / 1e3), ms_per_step=ms_dev / args.steps, clocks=clocks,
+               e2e=dict(value=tokens_per_step * args.steps / (ms_e2e / 1e3), unit="tokens/s",
+                        h2d_bytes_per_step=int(tmpl_host.numel() * 8), d2h_bytes_per_step=int(out_host.numel() * 8)),
+               gpu_launches=int(n_launch / max(1, (args.steps + args.warmup))) * args.steps)
+    res["roofline"] = sample_roofline(model, nb, res["ms_per_step"], args.gen_tokens)
+    res["params"] = param_count(model)
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def sample_roofline(model, nb, ms_per_step, gen_tokens):
+    """Dominant decode kernel = linear_small_m_kernel (weight streaming).  Algorithmic bytes per launch = the
+    bf16 weight matrix it reads (+ bias, x, y); timed live with CUDA events over one sweep of every layer's four
+    linears + the logits projection, i.e. the exact launch sequence of a decode step (7.9 GB >> the 126 MB L2,
+    so no weight is served from cache)."""
+    from cogview_b200 import ops
+    pk = peaks()
+    tr = model.transformer
+    h = tr.hidden_size
+    mats = []
+    for layer in tr.layers:
+        P = layer.param_list()
+        mats += [(P[2], P[3]), (P[4], P[5]), (P[10], P[11]), (P[12], P[13])]
+    mats.append((model.word_embeddings.weight, None))
+    xs = {h: torch.randn((nb, h), device="cuda").to(torch.bfloat16),
+          4 * h: torch.randn((nb, 4 * h), device="cuda").to(torch.bfloat16)}
+
+    def sweep():
+        for w, b in mats:
+            ops.linear_small_m(xs[w.shape[1]], w.detach(), None if b is None else b.detach())
+    for _ in range(2):
+        sweep()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        sweep()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = sum(w.numel() * 2 + (0 if b is None else b.numel() * 2) + nb * (w.shape[0] + w.shape[1]) * 2
+                 for w, b in mats)
+    achieved = nbytes / (ms / 1e3) / 1e9
+    return dict(kernel="linear_small_m_kernel", bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s",
+                frac=achieved / pk["hbm"], traffic=None, peak_source=pk["src"], launches_per_step=len(mats),
+                bytes_per_launch=nbytes / len(mats), avg_launch_us=ms * 1e3 / len(mats),
+                share_of_step=ms / (ms_per_step / gen_tokens), note="share_of_step = linear sweep / one decode step")
+
+
+# ----------------------------------------------------------------------------------------------------
+# training workload (configs[2])
+# ----------------------------------------------------------------------------------------------------
+def run_train(args, cfg, world, rank, dev_index, steps, warmup):
+    from cogview_b200 import mpu
+    from cogview_b200.model import (PyTorchDistributedDataParallel, gpt2_get_params_for_weight_decay_optimization)
+    from cogview_b200.optim import FusedAdamW
+    model = build_model(cfg, 0, "cuda").train()
+    groups = gpt2_get_params_for_weight_decay_optimization(model)
+    for g in groups:
+        g.setdefault("weight_decay", 0.01)
+    opt = FusedAdamW(groups, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0)
+    net = model
+    if world > 1:
+        net = PyTorchDistributedDataParallel(model, device_ids=[torch.cuda.current_device()],
+                                             gradient_as_bucket_view=True, bucket_cap_mb=200)
+    b, s = args.batch, cfg["max_sequence_length"] - 1
+    g = torch.Generator().manual_seed(100 + rank)
+    host_tokens = torch.cat((torch.randint(8192, 58192, (b, 64), generator=g),
+                             torch.randint(0, 8192, (b, s + 1 - 64), generator=g)), dim=1).pin_memory()
+    dev_tokens = host_tokens.cuda()
+    pos = torch.arange(s, device="cuda").unsqueeze(0).expand(b, -1).contiguous()
+    mask = torch.tril(torch.ones((1, 1, s, s), device="cuda"))
+    loss_host = torch.zeros(1).pin_memory()
+    last = {}
+
+    def one_step(tok):
+        tokens, labels = tok[:, :-1].contiguous(), tok[:, 1:].contiguous()
+        logits, *_ = net(tokens, pos, mask, None, None, 0)
+        losses = mpu.vocab_parallel_cross_entropy(logits, labels)
+        loss = losses.mean()
+        for p in model.parameters():
+            p.grad = None
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_dev():
+        last["loss"] = one_step(dev_tokens)
+
+    def step_e2e():
+        loss = one_step(host_tokens.cuda(non_blocking=True))
+        loss_host.copy_(loss.detach().float().view(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    tokens_per_step = b * s * world
+    l0 = launches()
+    ms_dev, clocks = timed(step_dev, steps, warmup, dev_index)
+    n_launch = launches() - l0
+    ms_e2e, _ = timed(step_e2e, steps, 1, dev_index)
+    loss_val = float(last["loss"].item())
+    assert loss_val == loss_val and loss_val < 20.0, "training loss is not finite"
+    L, h, V = cfg["num_layers"], cfg["hidden_size"], cfg["vocab_size"]
+    flops_per_token = 3 * (2 * 12 * L * h * h + 2 * h * V + 0.5 * 4 * L * s * h)
+    pk = peaks()
+    achieved = flops_per_token * tokens_per_step / world / (ms_dev / steps / 1e3) / 1e12
+    res = dict(value=tokens_per_step * steps / (ms_dev / 1e3), unit="tokens/s", ms_per_step=ms_dev / steps,
+               steps=steps, warmup=warmup, clocks=clocks, loss=loss_val,
+               e2e=dict(value=tokens_per_step * steps / (ms_e2e / 1e3), unit="tokens/s",
+                        h2d_bytes_per_step=int(host_tokens.numel() * 8), d2h_bytes_per_step=4),
+               gpu_launches=int(n_launch / max(1, steps + warmup)) * steps,
+               config=dict(workload="configs[2]: 4B training step, bf16, %d x %d tokens per GPU, dropout 0, AdamW + clip 1.0, "
+                                    "no activation recompute" % (b, s), global_batch=b * world,
+                           parallelism="dp%d" % world),
+               step_flops_per_gpu=flops_per_token * tokens_per_step / world,
+               roofline_step=dict(bound="tensor", achieved=achieved, peak=pk["tf_sust"], unit="TFLOP/s",
+                                  frac=achieved / pk["tf_sust"], peak_source=pk["src"],
+                                  note="whole step (all kernels) vs sustained cuBLAS bf16 peak"))
+    res["roofline"] = gemm_roofline(cfg, b * s)
+    del net, model, opt
+    torch.cuda.empty_cache()
+    return res
+
+
+def gemm_roofline(cfg, M):
+    """Dominant training kernel = gemm_kernel (tcgen05).  FLOPs per launch = 2*M*N*K; timed live with CUDA events
+    over the four forward GEMM shapes of a layer, rotating through 6 weight sets (> L2)."""
+    from cogview_b200 import ops
+    pk = peaks()
+    h = cfg["hidden_size"]
+    shapes = [("qkv", 3 * h, h), ("out", h, h), ("h_to_4h", 4 * h, h), ("4h_to_h", h, 4 * h)]
+    out = {}
+    tot_f, tot_ms, n = 0.0, 0.0, 0
+    for name, N, K in shapes:
+        ws = [torch.randn((N, K), device="cuda").to(torch.bfloat16) for _ in range(6)]
+        x = torch.randn((M, K), device="cuda").to(torch.bfloat16)
+        for w in ws[:2]:
+            ops.gemm(x, w)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            for w in ws:
+                ops.gemm(x, w)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 18
+        out[name] = dict(M=M, N=N, K=K, us=ms * 1e3, tflops=2.0 * M * N * K / ms / 1e9)
+        tot_f += 2.0 * M * N * K
+        tot_ms += ms
+        n += 1
+        del ws, x
+    achieved = tot_f / tot_ms / 1e9
+    return dict(kernel="gemm_kernel", bound="tensor", achieved=achieved, peak=pk["tf_burst"], unit="TFLOP/s",
+                frac=achieved / pk["tf_burst"], traffic=None, peak_source=pk["src"], shapes=out,
+                flops_per_launch=tot_f / n, avg_launch_us=tot_ms * 1e3 / n)
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference path on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(cfg, nb, gen_tokens, budget_s=20.0):
+    """Reference semantics (generation/sampling.py:147-151 over mpu/sparse_transformer.py:320,136-141): each step
+    re-normalises and re-projects the whole hidden-state memory.  Sample: ONE 4B-shaped layer (fp32) timed at a
+    few memory lengths with batch nb, cost fitted linearly in the memory length and integrated over the
+    generated positions x num_layers, plus the last-token logits GEMM per step."""
+    from oracle import cogview_oracle as O
+    from oracle import recipes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    one = dict(cfg)
+    one["num_layers"] = 1
+    sd = recipes.gpt2_state_dict(seed=1, perturb=False, **one)
+    sd = {k: v for k, v in sd.items()}
+    heads = cfg["num_attention_heads"]
+    h = cfg["hidden_size"]
+    pts = []
+    t_start = time.perf_counter()
+    with torch.no_grad():
+        for t in (64, 320, 576, 832, 1088):
+            mem = torch.randn((nb, t, h))
+            x = torch.randn((nb, 1, h))
+            mask = O.build_sep_mask(1, t + 1, 0)
+            O.transformer_layer(sd, 0, x, mask, heads, mem=mem)
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                O.transformer_layer(sd, 0, x, mask, heads, mem=mem)
+            pts.append((t, (time.perf_counter() - t0) / reps))
+            if time.perf_counter() - t_start > budget_s:
+                break
+        xl = torch.randn((nb, h))
+        t0 = time.perf_counter()
+        torch.nn.functional.linear(xl, sd["word_embeddings.weight"])
+        logits_s = time.perf_counter() - t0
+    # least-squares line  cost(t) = a + b t
+    n = len(pts)
+    mt, mc = sum(p[0] for p in pts) / n, sum(p[1] for p in pts) / n
+    bcoef = sum((p[0] - mt) * (p[1] - mc) for p in pts) / max(1e-12, sum((p[0] - mt) ** 2 for p in pts)) if n > 1 else 0.0
+    acoef = mc - bcoef * mt
+    ctx = 65
+    total = sum(cfg["num_layers"] * (acoef + bcoef * t) + logits_s for t in range(ctx, ctx + gen_tokens))
+    return dict(value=nb * gen_tokens / total, unit="tokens/s", cores=cores, kind="port",
+                sample="oracle port, fp32, %d threads: 1 of %d layers at memory lengths %s (batch %d), linear fit "
+                       "integrated over %d generated positions + logits GEMM per step; %.1f s of CPU work" % (
+                           cores, cfg["num_layers"], [p[0] for p in pts], nb, gen_tokens,
+                           time.perf_counter() - t_start))
+
+
+def cpu_baseline_train(cfg, budget_s=25.0):
+    from oracle import cogview_oracle as O
+    from oracle import recipes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    one = dict(cfg)
+    one["num_layers"] = 1
+    sd = {k: v.requires_grad_(True) for k, v in recipes.gpt2_state_dict(seed=1, perturb=False, **one).items()}
+    s = cfg["max_sequence_length"] - 1
+    h = cfg["hidden_size"]
+    x = torch.randn((1, s, h), requires_grad=True)
+    mask = torch.tril(torch.ones((1, 1, s, s)))
+    t0 = time.perf_counter()
+    y = O.transformer_layer(sd, 0, x, mask, cfg["num_attention_heads"])
+    y.sum().backward()
+    layer_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    hid = torch.randn((s, h), requires_grad=True)
+    logits = torch.nn.functional.linear(hid, sd["word_embeddings.weight"])
+    O.vocab_parallel_cross_entropy(logits, torch.randint(0, cfg["vocab_size"], (s,))).mean().backward()
+    head_s = time.perf_counter() - t0
+    total = cfg["num_layers"] * layer_s + head_s
+    return dict(value=s / total, unit="tokens/s", cores=cores, kind="port",
+                sample="oracle port, fp32, %d threads: 1 of %d layers fwd+bwd at b=1, s=%d (%.1f s) x %d + logits/CE "
+                       "fwd+bwd (%.1f s); extrapolated, optimizer not included" % (cores, cfg["num_layers"], s, layer_s,
+                                                                                  cfg["num_layers"], head_s))
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    cfg = MODEL_4B if args.model == "4b" else MODEL_TINY
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload_name = ("configs[1]: CogView-base 4B (48L, d=2560, 40H, V=58240), seq 1089, bf16, AR sampling: prefill 65 "
+                     "+ generate %d tokens, %d beams/GPU, top-k 200, KV cache + CUDA-graph decode" % (
+                         args.gen_tokens, args.batch))
+    base = dict(metric="tokens/sec (AR sample; train in `train`) CogView-4B seq1089", unit="tokens/s", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16", data="synthetic tokens, random-init weights")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        vals = []
+        for _ in range(max(1, min(args.steps, 2))):
+            cb = cpu_baseline_sample(cfg, args.batch, args.gen_tokens, budget_s=15.0)
+            vals.append(cb["value"])
+        cb["value"] = statistics.median(vals)
+        line = dict(base, impl="reference", value=cb["value"], ms_per_step=args.batch * args.gen_tokens / cb["value"] * 1e3,
+                    dtype="f32", cpu_baseline=cb, config=dict(workload=workload_name, parallelism="cpu"),
+                    e2e=dict(value=cb["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0, wall_s=time.perf_counter() - t0)
+        if args.workload in ("train", "both"):
+            line["train"] = dict(cpu_baseline=cpu_baseline_train(cfg))
+            line["train"]["value"] = line["train"]["cpu_baseline"]["value"]
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback (use --impl reference for the "
+                         "CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl")
+        from cogview_b200 import mpu
+        mpu.initialize_model_parallel(1)
+
+    line = dict(base)
+    if args.workload in ("sample", "both"):
+        r = run_sample(args, cfg, world, rank, local_rank)
+        line.update(value=r["value"], ms_per_step=r["ms_per_step"], e2e=r["e2e"], clocks=r["clocks"],
+                    gpu_launches=r["gpu_launches"], roofline=r["roofline"],
+                    config=dict(workload=workload_name, global_batch=args.batch * world, seq_len=1089,
+                                parallelism="dp%d (independent sequences per rank, no collective)" % world,
+                                l2="each decode step streams 7.9 GB of weights (>> 126 MB L2)", params=r["params"]))
+    if args.workload in ("train", "both"):
+        tsteps = args.train_steps or max(3, args.steps)
+        t = run_train(args, cfg, world, rank, local_rank, tsteps, max(3, args.warmup))
+        if args.workload == "train":
+            line.update(metric="tokens/sec (train) CogView-4B seq1089", value=t["value"], ms_per_step=t["ms_per_step"],
+                        e2e=t["e2e"], clocks=t["clocks"], gpu_launches=t["gpu_launches"], roofline=t["roofline"],
+                        config=t["config"], steps=t["steps"], warmup=t["warmup"])
+        line["train"] = t
+    if rank == 0:
+        if args.workload in ("sample", "both"):
+            line["cpu_baseline"] = cpu_baseline_sample(cfg, args.batch, args.gen_tokens)
+        if args.workload in ("train", "both"):
+            line["train"]["cpu_baseline"] = cpu_baseline_train(cfg)
+            if args.workload == "train":
+                line["cpu_baseline"] = line["train"]["cpu_baseline"]
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

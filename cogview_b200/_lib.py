@@ -38,6 +38,9 @@ def _declare(lib):
         "cv_attn_bwd": [P, L, L, P, L, L, P, L, L, P, P, P, P, P, I, I, I, I, I, P],
         "cv_linear_small_m": [P, L, P, L, P, P, L, I, I, P, I, I, I, P],
         "cv_attn_decode": [P, P, L, P, I, P, P, I, I, I, I, I, P],
+        "cv_adamw_step": [P, P, P, P, P, L, F, F, F, F, F, I, P, F, P],
+        "cv_sumsq_bf16": [P, L, P, P],
+        "cv_clip_coef": [P, F, P, P, P],
         "cv_embed_fwd": [P, P, P, P, P, P, I, I, P],
         "cv_embed_bwd": [P, P, P, P, P, I, I, P],
         "cv_cross_entropy_fwd": [P, L, P, P, P, P, I, I, P],
@@ -51,6 +54,7 @@ def _declare(lib):
     lib.cv_attn_bwd_workspace_bytes.restype = L
     lib.cv_attn_decode_workspace_bytes.argtypes = [I, I, I]
     lib.cv_attn_decode_workspace_bytes.restype = L
+    lib.cv_launch_count.restype = ctypes.c_longlong
     lib.cv_colsum_workspace_bytes.argtypes = [I]
     lib.cv_colsum_workspace_bytes.restype = L
     for name, args in sigs.items():

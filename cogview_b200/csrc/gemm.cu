@@ -272,6 +272,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cvh::fail_cuda("cv_gemm_bf16", e);
+    cvh::count_launches(1);
     return 0;
 }
 

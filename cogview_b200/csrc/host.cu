@@ -1,5 +1,6 @@
 #include "host.h"
 
+#include <atomic>
 #include <mutex>
 
 #include "../../include/cogview_b200.h"
@@ -23,6 +24,10 @@ int fail_cu(const char* fn, CUresult r) {
     last_error() = std::string(fn) + ": cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
     return -2;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
     static int n = 0;
@@ -95,5 +100,7 @@ extern "C" {
 const char* cv_last_error(void) { return cvh::last_error().c_str(); }
 
 int cv_version(void) { return CV_B200_VERSION; }
+
+long long cv_launch_count(void) { return cvh::launches(); }
 
 }

@@ -30,9 +30,12 @@ int fail_cu(const char* fn, CUresult r);                // driver error while en
     do {                                                       \
         cudaError_t _e = cudaGetLastError();                   \
         if (_e != cudaSuccess) return cvh::fail_cuda(__func__, _e); \
+        cvh::count_launches(1);                                \
     } while (0)
 
 int num_sms();
+void count_launches(int n);
+long long launches();   // kernels launched by this library since load (cv_launch_count)
 
 enum class Swizzle { None, B128 };
 

@@ -30,6 +30,8 @@ class DecodeRunner:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self.nsplit = max(1, min(16, -(-sms // (self.b * self.heads))))
         self.params = None
+        self.graph_launches = 0   # kernels per captured step
+        self.replays = 0
 
     def _gather_params(self):
         tr = self.model.transformer
@@ -80,10 +82,15 @@ class DecodeRunner:
                 self._run()
                 self._run()
             torch.cuda.current_stream().wait_stream(side)
+            from .._lib import lib
+            before = lib().cv_launch_count()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._run()
+            self.graph_launches = int(lib().cv_launch_count() - before)
             self.graph.replay()
+            self.replays += 1
         else:
             self.graph.replay()
+            self.replays += 1
         return self.logits

@@ -60,19 +60,25 @@ class _Caches:
 
 
 def prepare(owner, mems, b, sq):
-    """Find (or build) the cache that `mems` refers to and get it ready for sq more tokens."""
+    """Find (or build) the cache that `mems` refers to and get it ready for sq more tokens.  One cache (and its
+    captured decode graph) is kept per batch size and reused across sequences."""
     dev = owner.position_embeddings.weight.device
-    c = owner._kv
+    pool = owner.__dict__.setdefault('_kv_pool', {})
+    c = pool.get(b)
+    if c is not None and (c.maxlen != owner.max_memory_length or c.buf.device != dev):
+        c = None
     if not mems:
-        if c is None or c.b != b or c.maxlen != owner.max_memory_length or c.buf.device != dev:
+        if c is None:
             c = _Caches(owner, b, dev)
         c.t = 0
     elif c is not None and c.matches(mems, b):
         c.t = mems[0].size(1)
     else:
-        # beams were expanded / selected (generation/sampling.py:168-172, :188-198): materialise a new cache
-        c = _Caches(owner, b, dev)
+        # beams were expanded / selected (generation/sampling.py:168-172, :188-198): copy into this batch size's cache
+        if c is None:
+            c = _Caches(owner, b, dev)
         c.load_from(mems)
+    pool[b] = c
     owner._kv = c
     c.begin(sq)
     return c

@@ -476,9 +476,10 @@ class GPT2ParallelTransformer(torch.nn.Module):
         h = self.hidden_size
         keep_mems = self.max_memory_length > 0
         mode = self.mems_mode if keep_mems else None
-        mem_len = mems[0].size(1) if mems else 0
         if mems and torch.is_grad_enabled() and x.requires_grad:
             raise NotImplementedError('training with memory is not supported')
+        if mode == 'kv' and torch.is_grad_enabled() and x.requires_grad:
+            mode = 'hidden'   # training forward: return the reference's detached hidden-state mems
         hidden_mems = [x.detach().view(b, sq, h)] if mode == 'hidden' else []
         caches = kv_cache.prepare(self, mems, b, sq) if mode == 'kv' else None
         for i, layer in enumerate(self.layers):

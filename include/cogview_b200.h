@@ -26,6 +26,8 @@ extern "C" {
 
 int cv_version(void);
 const char* cv_last_error(void);
+/* number of kernels this library has launched since it was loaded (host-side counter) */
+long long cv_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  C[M,N] = op(A)[M,K] * op(B)[N,K]^T (+ bias[N]) (+ tanh-GELU)      tcgen05 + TMA + TMEM
@@ -128,6 +130,18 @@ int64_t cv_attn_decode_workspace_bytes(int b, int heads, int nsplit);
 int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_stride, const int* cur_len_dev, int cur_len,
                    void* out, float* workspace, int b, int heads, int head_dim, int max_len, int nsplit,
                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step: fused AdamW on bf16 parameters with fp32 master weights / moments — replaces
+ * FP16_Optimizer.step + apex FusedAdam (fp16/fp16.py:399-453, pretrain_gpt2.py:139-140; decoupled weight decay)
+ * and, with cv_sumsq_bf16 + cv_clip_coef, the global-norm clipping of mpu/grads.py:28-74.
+ *   grad_scale_dev: NULL or device float multiplied into the gradient (the clip coefficient); step >= 1.
+ * ---------------------------------------------------------------------------------------------- */
+int cv_adamw_step(void* param, const void* grad, float* master, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, const float* grad_scale_dev,
+                  float grad_scale, void* stream);
+int cv_sumsq_bf16(const void* x, int64_t n, float* out, void* stream);   /* *out += sum(x^2) */
+int cv_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
 
 #ifdef __cplusplus
 }

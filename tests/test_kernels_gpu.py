@@ -181,3 +181,24 @@ def test_attention_bwd_matches_autograd_of_standard_attention(ops, b, heads, s, 
                             ("dv", dqkv[..., 2 * h:], vr.grad)):
         e = rel_err(got, want)
         assert e < 3e-2, (name, e)
+
+
+def test_fused_adamw_matches_torch_adamw_on_fp32_masters(ops):
+    from cogview_b200.optim import FusedAdamW
+    g = torch.Generator().manual_seed(11)
+    w0 = torch.randn((300, 257), generator=g)
+    p = torch.nn.Parameter(bf(w0).cuda())
+    ref = torch.nn.Parameter(bf(w0).float())
+    opt = FusedAdamW([{'params': [p], 'weight_decay': 0.01}], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, max_grad_norm=1.0)
+    ropt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.01)
+    for it in range(3):
+        gr = bf(torch.randn((300, 257), generator=g))
+        p.grad = gr.cuda()
+        ref.grad = gr.float().clone()
+        gn = torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        ropt.step()
+        assert abs(opt.last_grad_norm.item() - gn.item()) < 1e-3 * gn.item()
+    master = opt.state[p]['master'].cpu()
+    assert (master - ref.detach()).abs().max().item() < 1e-5
+    assert torch.equal(p.detach().cpu(), bf(master))
