@@ -16,11 +16,20 @@ namespace {
 using namespace cv;
 
 // ------------------------------------------------------------------------------------------------
-// skinny linear
+// skinny linear on warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 x bf16 -> fp32).
+//
+// A CTA owns 16 output columns (16 rows of W); its 8 warps split K, so a 2560-column layer still puts
+// 160 x 8 warps on the machine.  Per 32-element K chunk a lane issues two 16-byte loads of W (rows g and g+8,
+// elements 8q..8q+7; g = lane/4, q = lane%4) and one 16-byte load of x (row g): because a dot product does not
+// care in which order k is summed, those 8 contiguous elements are fed to two MMAs as the fragment slots
+// {2q,2q+1,2q+8,2q+9}, with x permuted identically — so both operands are read with full 16-byte, sector-exact
+// loads straight from global/L2 into MMA fragments (no shared memory, no conversions, ~10 instructions per KB of
+// weights).  Four chunks (4 KB of W per warp) are in flight while the previous four are consumed.
+// Partial [16 x 8] tiles of the 8 warps are reduced through shared memory; bias / GELU / abs-max in the epilogue.
 // ------------------------------------------------------------------------------------------------
-constexpr int SK_WARPS = 4;
-constexpr int SK_COLS = 4;        // output columns per warp
-constexpr int SK_KC = 2048;       // K chunk staged in shared memory
+constexpr int SK_WARPS = 8;
+constexpr int SK_NT = 16;         // output columns per CTA
+constexpr int SK_UNROLL = 4;      // K chunks (of 32) per register stage
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -30,77 +39,206 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
         f[2 * t + 1] = __high2float(p[t]);
     }
 }
+__device__ __forceinline__ uint4 ld_stream(const void* p) {   // read-once data: do not keep it in L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
-template <int MT>
+struct SkStage {
+    uint4 w0[SK_UNROLL], w1[SK_UNROLL], xv[SK_UNROLL];
+};
+
 __global__ void __launch_bounds__(SK_WARPS * 32)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ W,
                       int64_t ldw, const __nv_bfloat16* __restrict__ bias, void* __restrict__ out, int64_t ldo,
                       int out_f32, int act, float* __restrict__ absmax, int M, int N, int K) {
-    __shared__ __align__(16) __nv_bfloat16 xs[MT][SK_KC];
+    __shared__ float part[SK_WARPS][SK_NT][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = (blockIdx.x * SK_WARPS + warp) * SK_COLS;
-    float acc[MT][SK_COLS];
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int c = 0; c < SK_COLS; ++c) acc[m][c] = 0.f;
+    const int g = lane >> 2, q = lane & 3;
+    const int n0 = blockIdx.x * SK_NT;
+    const int nchunks = (K + 31) / 32;
+    const int per_warp = (nchunks + SK_WARPS - 1) / SK_WARPS;
+    const int c_begin = warp * per_warp, c_end = min(nchunks, c_begin + per_warp);
+    const bool r0_ok = n0 + g < N, r1_ok = n0 + g + 8 < N, x_ok = g < M;
+    const __nv_bfloat16* wrow0 = W + (size_t)(n0 + g) * ldw + q * 8;
+    const __nv_bfloat16* wrow1 = W + (size_t)(n0 + g + 8) * ldw + q * 8;
+    const __nv_bfloat16* xrow = x + (size_t)g * ldx + q * 8;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
 
-    for (int kc = 0; kc < K; kc += SK_KC) {
-        const int klen = min(SK_KC, K - kc);
-        __syncthreads();
-        for (int i = threadIdx.x * 8; i < MT * SK_KC; i += SK_WARPS * 32 * 8) {
-            const int m = i / SK_KC, k = i % SK_KC;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (m < M && k < klen) v = *reinterpret_cast<const uint4*>(x + (size_t)m * ldx + kc + k);
-            *reinterpret_cast<uint4*>(&xs[m][k]) = v;
+    auto load_stage = [&](int c0, SkStage& st) {
+#pragma unroll
+        for (int u = 0; u < SK_UNROLL; ++u) {
+            const int c = c0 + u;
+            const int k = c * 32 + q * 8;
+            const bool in = c < c_end && k < K;
+            st.w0[u] = (in && r0_ok) ? ld_stream(wrow0 + (size_t)c * 32) : zero;
+            st.w1[u] = (in && r1_ok) ? ld_stream(wrow1 + (size_t)c * 32) : zero;
+            st.xv[u] = (in && x_ok) ? *reinterpret_cast<const uint4*>(xrow + (size_t)c * 32) : zero;
         }
-        __syncthreads();
-        if (n0 < N) {
-            for (int k = lane * 8; k < klen; k += 256) {
-                float w[SK_COLS][8];
+    };
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    auto consume = [&](const SkStage& st) {
 #pragma unroll
-                for (int c = 0; c < SK_COLS; ++c) {
-                    uint4 u = make_uint4(0, 0, 0, 0);
-                    if (n0 + c < N) u = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(n0 + c) * ldw + kc + k));
-                    bf16x8_to_float(u, w[c]);
-                }
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    float xv[8];
-                    bf16x8_to_float(*reinterpret_cast<const uint4*>(&xs[m][k]), xv);
-#pragma unroll
-                    for (int c = 0; c < SK_COLS; ++c) {
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) acc[m][c] = fmaf(w[c][t], xv[t], acc[m][c]);
-                    }
-                }
-            }
+        for (int u = 0; u < SK_UNROLL; ++u) {
+            mma_bf16_16816(d, st.w0[u].x, st.w1[u].x, st.w0[u].y, st.w1[u].y, st.xv[u].x, st.xv[u].y);
+            mma_bf16_16816(d, st.w0[u].z, st.w1[u].z, st.w0[u].w, st.w1[u].w, st.xv[u].z, st.xv[u].w);
         }
+    };
+    SkStage sa, sb;
+    load_stage(c_begin, sa);
+    load_stage(c_begin + SK_UNROLL, sb);
+    for (int c = c_begin; c < c_end; c += 2 * SK_UNROLL) {
+        consume(sa);
+        load_stage(c + 2 * SK_UNROLL, sa);
+        consume(sb);
+        load_stage(c + 3 * SK_UNROLL, sb);
     }
-    if (n0 >= N) return;
+    // D fragment: d0,d1 = (row g, cols 2q,2q+1), d2,d3 = (row g+8, cols 2q,2q+1); row = output column, col = m
+    part[warp][g][2 * q] = d[0];
+    part[warp][g][2 * q + 1] = d[1];
+    part[warp][g + 8][2 * q] = d[2];
+    part[warp][g + 8][2 * q + 1] = d[3];
+    __syncthreads();
     float tmax = 0.f;
+    if (threadIdx.x < SK_NT * 8) {
+        const int m = threadIdx.x >> 4, nn = threadIdx.x & 15;   // consecutive threads -> consecutive columns
+        float v = 0.f;
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-#pragma unroll
-        for (int c = 0; c < SK_COLS; ++c) {
-            float v = warp_sum(acc[m][c]);
-            if (lane == m * SK_COLS + c && m < M && n0 + c < N) {
-                if (bias != nullptr) v += __bfloat162float(bias[n0 + c]);
-                if (act == 1) v = gelu_tanh(v);
-                if (out_f32) {
-                    static_cast<float*>(out)[(size_t)m * ldo + n0 + c] = v;
-                    tmax = fabsf(v);
-                } else {
-                    __nv_bfloat16 o = __float2bfloat16_rn(v);
-                    static_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + n0 + c] = o;
-                    tmax = fabsf(__bfloat162float(o));
-                }
+        for (int w = 0; w < SK_WARPS; ++w) v += part[w][nn][m];
+        const int n = n0 + nn;
+        if (m < M && n < N) {
+            if (bias != nullptr) v += __bfloat162float(bias[n]);
+            if (act == 1) v = gelu_tanh(v);
+            if (out_f32) {
+                static_cast<float*>(out)[(size_t)m * ldo + n] = v;
+                tmax = fabsf(v);
+            } else {
+                const __nv_bfloat16 o = __float2bfloat16_rn(v);
+                static_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + n] = o;
+                tmax = fabsf(__bfloat162float(o));
             }
         }
     }
-    if (absmax != nullptr) {
+    if (absmax != nullptr && warp < 4) {
         tmax = warp_max(tmax);
         if (lane == 0 && tmax > 0.f) atomic_max_nonneg(absmax, tmax);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sandwich-LN glue between two decode linears, one CTA for the whole [M, K] (M <= 16):
+//   y  = res_in + LN_post(gemm_out / (max|gemm_out| / 8))       (third / fourth LayerNorm + residual add)
+//   xn = LN_pre(y / (max|y| / 8))                               (post-attention / next input / final LayerNorm)
+// mpu/sparse_transformer.py:326-331 and :337-340 + :319 of the next layer; max|y| is taken inside the CTA
+// (the whole tensor is here), max|gemm_out| comes from the linear kernel that produced it.
+// ------------------------------------------------------------------------------------------------
+constexpr int LP_THREADS = 1024;
+template <int MT>
+__global__ void __launch_bounds__(LP_THREADS)
+ln_pair_kernel(const float* __restrict__ res_in, const __nv_bfloat16* __restrict__ gemm_out,
+               const float* __restrict__ absmax_gemm, const __nv_bfloat16* __restrict__ g_post,
+               const __nv_bfloat16* __restrict__ b_post, const __nv_bfloat16* __restrict__ g_pre,
+               const __nv_bfloat16* __restrict__ b_pre, float eps, float* __restrict__ res_out,
+               __nv_bfloat16* __restrict__ xn_out, int M, int K) {
+    constexpr int WPR = 32 / MT;               // warps per row
+    constexpr int TPR = WPR * 32;              // threads per row
+    constexpr int MAXE = MT <= 4 ? 16 : (MT == 8 ? 24 : 40);   // elements per thread (K <= TPR * MAXE)
+    __shared__ float red[MT][WPR];
+    __shared__ float bcast[MT];
+    __shared__ float smax[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = warp / WPR, wr = warp % WPR;
+    const int tr = wr * 32 + lane;             // thread index within the row group
+    const bool row_ok = row < M;
+    float v[MAXE];
+    int ne = 0;
+    for (int k = tr; k < K; k += TPR) ++ne;    // same for all passes
+
+    auto row_sum = [&](float s) -> float {     // sum over the row group, broadcast to its threads
+        s = warp_sum(s);
+        if (lane == 0) red[row][wr] = s;
+        __syncthreads();
+        if (wr == 0 && lane == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < WPR; ++i) t += red[row][i];
+            bcast[row] = t;
+        }
+        __syncthreads();
+        const float r = bcast[row];
+        __syncthreads();
+        return r;
+    };
+    const float inv_k = 1.0f / K;
+    // ---- y = res_in (+ LN_post(gemm_out)) ----
+    if (gemm_out != nullptr) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) {
+            const int k = tr + e * TPR;
+            v[e] = (e < ne && row_ok) ? __bfloat162float(gemm_out[(size_t)row * K + k]) : 0.f;
+            s += v[e];
+        }
+        const float mean = row_sum(s) * inv_k;
+        float ss = 0.f;
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) if (e < ne) { const float d = v[e] - mean; ss += d * d; }
+        const float var = row_sum(ss) * inv_k;
+        const float c = *absmax_gemm * 0.125f;
+        const float rstd = rsqrtf(var + eps * c * c);
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) {
+            const int k = tr + e * TPR;
+            if (e < ne && row_ok)
+                v[e] = (v[e] - mean) * rstd * __bfloat162float(g_post[k]) + __bfloat162float(b_post[k]) +
+                       res_in[(size_t)row * K + k];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) {
+            const int k = tr + e * TPR;
+            v[e] = (e < ne && row_ok) ? res_in[(size_t)row * K + k] : 0.f;
+        }
+    }
+    float mx = 0.f, s = 0.f;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+        const int k = tr + e * TPR;
+        if (e < ne && row_ok) {
+            if (res_out != nullptr) res_out[(size_t)row * K + k] = v[e];
+            mx = fmaxf(mx, fabsf(v[e]));
+            s += v[e];
+        }
+    }
+    // ---- max|y| over the whole tensor ----
+    mx = warp_max(mx);
+    if (lane == 0) smax[warp] = mx;
+    __syncthreads();
+    float am = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) am = fmaxf(am, smax[i]);
+    // ---- xn = LN_pre(y) ----
+    const float mean = row_sum(s) * inv_k;
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) if (e < ne && row_ok) { const float d = v[e] - mean; ss += d * d; }
+    const float var = row_sum(ss) * inv_k;
+    const float c = am * 0.125f;
+    const float rstd = rsqrtf(var + eps * c * c);
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+        const int k = tr + e * TPR;
+        if (e < ne && row_ok)
+            xn_out[(size_t)row * K + k] =
+                __float2bfloat16_rn((v[e] - mean) * rstd * __bfloat162float(g_pre[k]) + __bfloat162float(b_pre[k]));
     }
 }
 
@@ -233,28 +371,47 @@ extern "C" int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int6
     CV_REQUIRE(x && W && out, "null pointer");
     CV_REQUIRE(M >= 1 && M <= 16, "cv_linear_small_m handles 1 <= M <= 16 rows (use cv_gemm_bf16 above that)");
     CV_REQUIRE(N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "K, ldx, ldw must be multiples of 8");
+    CV_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+               "x and W must be 16-byte aligned");
     CV_REQUIRE(act == 0 || act == 1, "act must be 0 or 1");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int cols_per_block = SK_WARPS * SK_COLS;
-    const int grid = (N + cols_per_block - 1) / cols_per_block;
+    const int grid = (N + SK_NT - 1) / SK_NT;
     const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
     const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(W);
     const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(bias);
-#define LAUNCH(MT) linear_small_m_kernel<MT><<<grid, SK_WARPS * 32, 0, s>>>(xb, ldx, wb, ldw, bb, out, ldo, out_is_f32, act, absmax, M, N, K)
+    const size_t osz = out_is_f32 ? 4 : 2;
+    // the MMA N dimension holds up to 8 batch rows; 9..16 rows take a second pass over the weights
+    for (int m0 = 0; m0 < M; m0 += 8) {
+        const int mm = (M - m0) < 8 ? (M - m0) : 8;
+        linear_small_m_kernel<<<grid, SK_WARPS * 32, 0, s>>>(xb + (size_t)m0 * ldx, ldx, wb, ldw, bb,
+                                                            static_cast<char*>(out) + (size_t)m0 * ldo * osz, ldo,
+                                                            out_is_f32, act, absmax, mm, N, K);
+        CV_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int cv_ln_pair_small_m(const float* res_in, const void* gemm_out, const float* absmax_gemm,
+                                  const void* g_post, const void* b_post, const void* g_pre, const void* b_pre,
+                                  float eps, float* res_out, void* xn_out, int M, int K, void* stream) {
+    CV_REQUIRE(res_in && g_pre && b_pre && xn_out, "null pointer");
+    CV_REQUIRE(gemm_out == nullptr || (absmax_gemm && g_post && b_post), "gemm_out needs absmax_gemm, g_post, b_post");
+    CV_REQUIRE(M >= 1 && M <= 16 && K > 0, "1 <= M <= 16");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* go = static_cast<const __nv_bfloat16*>(gemm_out);
+    const __nv_bfloat16 *gp = static_cast<const __nv_bfloat16*>(g_post), *bp = static_cast<const __nv_bfloat16*>(b_post);
+    const __nv_bfloat16 *gq = static_cast<const __nv_bfloat16*>(g_pre), *bq = static_cast<const __nv_bfloat16*>(b_pre);
+    __nv_bfloat16* xo = static_cast<__nv_bfloat16*>(xn_out);
+#define LAUNCH(MT)                                                                                              \
+    do {                                                                                                        \
+        CV_REQUIRE(K <= (32 / MT) * 32 * (MT <= 4 ? 16 : (MT == 8 ? 24 : 40)), "K too large for cv_ln_pair_small_m");                   \
+        ln_pair_kernel<MT><<<1, LP_THREADS, 0, s>>>(res_in, go, absmax_gemm, gp, bp, gq, bq, eps, res_out, xo, M, K); \
+    } while (0)
     if (M == 1) LAUNCH(1);
     else if (M == 2) LAUNCH(2);
     else if (M <= 4) LAUNCH(4);
     else if (M <= 8) LAUNCH(8);
-    else {
-        // 16 rows x 2048 x 2 B = 64 KB of static smem would exceed the 48 KB static limit: two passes of 8 rows
-        LAUNCH(8);
-        CV_LAUNCH_CHECK();
-        const int M2 = M - 8;
-        const size_t osz = out_is_f32 ? 4 : 2;
-        linear_small_m_kernel<8><<<grid, SK_WARPS * 32, 0, s>>>(xb + 8 * ldx, ldx, wb, ldw, bb,
-                                                              static_cast<char*>(out) + 8 * ldo * osz, ldo,
-                                                              out_is_f32, act, absmax, M2, N, K);
-    }
+    else LAUNCH(16);
 #undef LAUNCH
     CV_LAUNCH_CHECK();
     return 0;

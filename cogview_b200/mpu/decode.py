@@ -45,26 +45,28 @@ class DecodeRunner:
     def _run(self):
         b, h, heads = self.b, self.h, self.heads
         L = len(self.params)
-        scal = ops.new_scalars(4 * L + 1, self.ids.device)
-        x = ops.embed_fwd(self.ids, self.pos, self.wte, self.wpe, scal[4 * L:4 * L + 1])
-        am = scal[4 * L:4 * L + 1]
+        scal = ops.new_scalars(2 * L + 1, self.ids.device)
+        x = ops.embed_fwd(self.ids, self.pos, self.wte, self.wpe, scal[2 * L:2 * L + 1])
+        prev_gemm = prev_am = prev_post = None
         for i, P in enumerate(self.params):
             (g1, b1, wqkv, bqkv, wd, bd, g3, b3, g2, b2, w1, bb1, w2, bb2, g4, b4) = P
-            s = scal[4 * i:4 * i + 4]
-            ln1, _, _ = ops.layernorm_absmax_fwd(x, am, g1, b1, self.eps)
-            qkv = ops.linear_small_m(ln1, wqkv, bqkv)
+            s = scal[2 * i:2 * i + 2]
+            # x_i = x_{i-1} + LN4(mlp_out_{i-1});  xn = LN1(x_i)
+            y, xn = ops.ln_pair_small_m(x, prev_gemm, prev_am, prev_post, (g1, b1), self.eps,
+                                        want_res_out=prev_gemm is not None)
+            if y is not None:
+                x = y
+            qkv = ops.linear_small_m(xn, wqkv, bqkv)
             ctx = ops.attn_decode(qkv, self.caches.buf[i], heads, cur_len_dev=self.cur_len, nsplit=self.nsplit)
             attn_out = ops.linear_small_m(ctx, wd, bd, absmax=s[0:1])
-            y, _, _ = ops.layernorm_absmax_fwd(attn_out, s[0:1], g3, b3, self.eps, residual=x,
-                                               out_dtype=torch.float32, absmax_out=s[1:2])
-            ln2, _, _ = ops.layernorm_absmax_fwd(y, s[1:2], g2, b2, self.eps)
-            h4 = ops.linear_small_m(ln2, w1, bb1, act=ops.ACT_GELU)
-            mlp_out = ops.linear_small_m(h4, w2, bb2, absmax=s[2:3])
-            x, _, _ = ops.layernorm_absmax_fwd(mlp_out, s[2:3], g4, b4, self.eps, residual=y,
-                                               out_dtype=torch.float32, absmax_out=s[3:4])
-            am = s[3:4]
-        yf, _, _ = ops.layernorm_absmax_fwd(x, am, self.fl[0], self.fl[1], self.fl[2])
-        self.logits = ops.linear_small_m(yf, self.wte, out_dtype=torch.float32)
+            # y = x + LN3(attn_out);  xn2 = LN2(y)
+            x, xn2 = ops.ln_pair_small_m(x, attn_out, s[0:1], (g3, b3), (g2, b2), self.eps)
+            h4 = ops.linear_small_m(xn2, w1, bb1, act=ops.ACT_GELU)
+            prev_gemm = ops.linear_small_m(h4, w2, bb2, absmax=s[1:2])
+            prev_am, prev_post = s[1:2], (g4, b4)
+        _, xf = ops.ln_pair_small_m(x, prev_gemm, prev_am, prev_post, (self.fl[0], self.fl[1]), self.fl[2],
+                                    want_res_out=False)
+        self.logits = ops.linear_small_m(xf, self.wte, out_dtype=torch.float32)
 
     def step(self, ids, pos, t):
         """ids, pos: [b, 1] int64; t: tokens already cached.  Returns logits [b, V] fp32 (a static buffer)."""

@@ -244,3 +244,18 @@ def attn_decode(qkv, cache, heads, *, cur_len=None, cur_len_dev=None, nsplit=1, 
                               cache.shape[1], nsplit, stream_ptr())
     check(rc, "cv_attn_decode")
     return out
+
+
+def ln_pair_small_m(res_in, gemm_out, absmax_gemm, post, pre, eps, *, want_res_out=True):
+    """y = res_in + LN_post(gemm_out) (gemm_out may be None), xn = LN_pre(y).  post/pre: (gamma, beta) bf16.
+    Returns (y fp32 or None, xn bf16)."""
+    require_cuda(res_in, gemm_out)
+    M, K = res_in.shape
+    assert res_in.dtype == torch.float32 and res_in.is_contiguous()
+    y = torch.empty_like(res_in) if want_res_out else None
+    xn = torch.empty((M, K), dtype=torch.bfloat16, device=res_in.device)
+    gp, bp = post if post is not None else (None, None)
+    rc = lib().cv_ln_pair_small_m(ptr(res_in), ptr(gemm_out), ptr(absmax_gemm), ptr(gp), ptr(bp), ptr(pre[0]),
+                                  ptr(pre[1]), float(eps), ptr(y), ptr(xn), M, K, stream_ptr())
+    check(rc, "cv_ln_pair_small_m")
+    return y, xn

@@ -126,6 +126,12 @@ int cv_colsum_bf16(const void* dy, int64_t ld, void* out, float* workspace, int 
  * ---------------------------------------------------------------------------------------------- */
 int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out,
                       int64_t ldo, int out_is_f32, int act, float* absmax, int M, int N, int K, void* stream);
+/* Sandwich-LN glue between two decode linears (M <= 16, one CTA): y = res_in + LN_post(gemm_out) (skipped when
+ * gemm_out is NULL), xn = LN_pre(y) with both abs-max pre-scales (mpu/sparse_transformer.py:40-44, :319-331, :337-340).
+ * res_out (fp32, may be NULL) receives y; xn_out (bf16) feeds the next linear. */
+int cv_ln_pair_small_m(const float* res_in, const void* gemm_out, const float* absmax_gemm, const void* g_post,
+                       const void* b_post, const void* g_pre, const void* b_pre, float eps, float* res_out,
+                       void* xn_out, int M, int K, void* stream);
 int64_t cv_attn_decode_workspace_bytes(int b, int heads, int nsplit);
 int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_stride, const int* cur_len_dev, int cur_len,
                    void* out, float* workspace, int b, int heads, int head_dim, int max_len, int nsplit,

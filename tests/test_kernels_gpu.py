@@ -202,3 +202,36 @@ def test_fused_adamw_matches_torch_adamw_on_fp32_masters(ops):
     master = opt.state[p]['master'].cpu()
     assert (master - ref.detach()).abs().max().item() < 1e-5
     assert torch.equal(p.detach().cpu(), bf(master))
+
+
+@pytest.mark.parametrize("M,N,K,act", [(4, 7680, 2560, 0), (4, 2560, 10240, 0), (2, 1024, 256, 1), (1, 58240, 256, 0),
+                                       (8, 2560, 2560, 0), (13, 520, 264, 0)])
+def test_linear_small_m(ops, M, N, K, act):
+    g = torch.Generator().manual_seed(M + N)
+    x, w, bias = bf(torch.randn((M, K), generator=g)), bf(torch.randn((N, K), generator=g) * 0.05), bf(
+        torch.randn(N, generator=g))
+    ref = x.float() @ w.float().t() + bias.float()
+    if act:
+        ref = O.gelu(ref)
+    am = torch.zeros(1, device="cuda")
+    out = ops.linear_small_m(x.cuda(), w.cuda(), bias.cuda(), act=act, absmax=am)
+    assert rel_err(out, ref) < 1e-2
+    assert am.item() == out.float().abs().max().item()
+    out32 = ops.linear_small_m(x.cuda(), w.cuda(), bias.cuda(), act=act, out_dtype=torch.float32)
+    assert rel_err(out32, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,K", [(4, 2560), (2, 256), (1, 2560), (7, 512), (16, 2560)])
+def test_ln_pair_small_m(ops, M, K):
+    g = torch.Generator().manual_seed(M * K)
+    res = torch.randn((M, K), generator=g)
+    go = bf(torch.randn((M, K), generator=g) * 5)
+    gp, bp = bf(1 + 0.1 * torch.randn(K, generator=g)), bf(0.1 * torch.randn(K, generator=g))
+    gq, bq = bf(1 + 0.1 * torch.randn(K, generator=g)), bf(0.1 * torch.randn(K, generator=g))
+    y_ref = res + O.layernorm_absmax(go.float(), gp.float(), bp.float())
+    xn_ref = O.layernorm_absmax(y_ref, gq.float(), bq.float())
+    am = ops.absmax(go.cuda())
+    y, xn = ops.ln_pair_small_m(res.cuda(), go.cuda(), am, (gp.cuda(), bp.cuda()), (gq.cuda(), bq.cuda()), 1e-5)
+    assert rel_err(y, y_ref) < 1e-5 and rel_err(xn, xn_ref) < 1e-2
+    _, xn0 = ops.ln_pair_small_m(res.cuda(), None, None, None, (gq.cuda(), bq.cuda()), 1e-5, want_res_out=False)
+    assert rel_err(xn0, O.layernorm_absmax(res, gq.float(), bq.float())) < 1e-2
