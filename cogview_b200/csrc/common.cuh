@@ -39,6 +39,11 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Programmatic dependent launch: let the next kernel in the stream start its prologue now / wait until the
+// previous kernel has completed and its writes are visible.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // atomic max on a non-negative float stored as its bit pattern (monotone for x >= 0)
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
     atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));

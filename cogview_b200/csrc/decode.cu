@@ -39,10 +39,17 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
         f[2 * t + 1] = __high2float(p[t]);
     }
 }
-__device__ __forceinline__ uint4 ld_stream(const void* p) {   // read-once data: do not keep it in L1
+// weights are read once per step: bypass L1 and mark the L2 lines evict-first so that the small hot tensors
+// (activations, LayerNorm parameters, abs-max scalars) stay L2-resident while 7.9 GB of weights stream through
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ld_stream(const void* p, uint64_t pol) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -73,16 +80,27 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
     const __nv_bfloat16* xrow = x + (size_t)g * ldx + q * 8;
     const uint4 zero = make_uint4(0, 0, 0, 0);
 
-    auto load_stage = [&](int c0, SkStage& st) {
+    const uint64_t pol = make_evict_first_policy();
+    auto load_w = [&](int c0, SkStage& st) {
 #pragma unroll
         for (int u = 0; u < SK_UNROLL; ++u) {
             const int c = c0 + u;
-            const int k = c * 32 + q * 8;
-            const bool in = c < c_end && k < K;
-            st.w0[u] = (in && r0_ok) ? ld_stream(wrow0 + (size_t)c * 32) : zero;
-            st.w1[u] = (in && r1_ok) ? ld_stream(wrow1 + (size_t)c * 32) : zero;
+            const bool in = c < c_end && c * 32 + q * 8 < K;
+            st.w0[u] = (in && r0_ok) ? ld_stream(wrow0 + (size_t)c * 32, pol) : zero;
+            st.w1[u] = (in && r1_ok) ? ld_stream(wrow1 + (size_t)c * 32, pol) : zero;
+        }
+    };
+    auto load_x = [&](int c0, SkStage& st) {
+#pragma unroll
+        for (int u = 0; u < SK_UNROLL; ++u) {
+            const int c = c0 + u;
+            const bool in = c < c_end && c * 32 + q * 8 < K;
             st.xv[u] = (in && x_ok) ? *reinterpret_cast<const uint4*>(xrow + (size_t)c * 32) : zero;
         }
+    };
+    auto load_stage = [&](int c0, SkStage& st) {
+        load_w(c0, st);
+        load_x(c0, st);
     };
     float d[4] = {0.f, 0.f, 0.f, 0.f};
     auto consume = [&](const SkStage& st) {
@@ -93,8 +111,14 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
         }
     };
     SkStage sa, sb;
-    load_stage(c_begin, sa);
-    load_stage(c_begin + SK_UNROLL, sb);
+    // weights do not depend on the previous kernel: request them, let the next kernel start its own prologue,
+    // and only then wait for the producer of x
+    load_w(c_begin, sa);
+    load_w(c_begin + SK_UNROLL, sb);
+    pdl_launch_dependents();
+    pdl_wait();
+    load_x(c_begin, sa);
+    load_x(c_begin + SK_UNROLL, sb);
     for (int c = c_begin; c < c_end; c += 2 * SK_UNROLL) {
         consume(sa);
         load_stage(c + 2 * SK_UNROLL, sa);
@@ -141,7 +165,8 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
 // (the whole tensor is here), max|gemm_out| comes from the linear kernel that produced it.
 // ------------------------------------------------------------------------------------------------
 constexpr int LP_THREADS = 1024;
-template <int MT>
+// MT: padded row count (warps are split evenly over the rows); NP: bf16 pairs per thread (K <= 2 * NP * threads/row)
+template <int MT, int NP>
 __global__ void __launch_bounds__(LP_THREADS)
 ln_pair_kernel(const float* __restrict__ res_in, const __nv_bfloat16* __restrict__ gemm_out,
                const float* __restrict__ absmax_gemm, const __nv_bfloat16* __restrict__ g_post,
@@ -150,95 +175,120 @@ ln_pair_kernel(const float* __restrict__ res_in, const __nv_bfloat16* __restrict
                __nv_bfloat16* __restrict__ xn_out, int M, int K) {
     constexpr int WPR = 32 / MT;               // warps per row
     constexpr int TPR = WPR * 32;              // threads per row
-    constexpr int MAXE = MT <= 4 ? 16 : (MT == 8 ? 24 : 40);   // elements per thread (K <= TPR * MAXE)
-    __shared__ float red[MT][WPR];
-    __shared__ float bcast[MT];
+    __shared__ float red[4][MT][WPR];
     __shared__ float smax[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = warp / WPR, wr = warp % WPR;
     const int tr = wr * 32 + lane;             // thread index within the row group
     const bool row_ok = row < M;
-    float v[MAXE];
-    int ne = 0;
-    for (int k = tr; k < K; k += TPR) ++ne;    // same for all passes
+    const bool has_post = gemm_out != nullptr;
 
-    auto row_sum = [&](float s) -> float {     // sum over the row group, broadcast to its threads
-        s = warp_sum(s);
-        if (lane == 0) red[row][wr] = s;
-        __syncthreads();
-        if (wr == 0 && lane == 0) {
-            float t = 0.f;
+    // LayerNorm parameters are static: fetch them (packed bf16x2) before waiting for the producer kernel
+    uint32_t gq[NP], bq[NP], gp[NP], bp[NP];
 #pragma unroll
-            for (int i = 0; i < WPR; ++i) t += red[row][i];
-            bcast[row] = t;
-        }
+    for (int e = 0; e < NP; ++e) {
+        const int k = 2 * (tr + e * TPR);
+        const bool ok = k < K;
+        gq[e] = ok ? *reinterpret_cast<const uint32_t*>(g_pre + k) : 0u;
+        bq[e] = ok ? *reinterpret_cast<const uint32_t*>(b_pre + k) : 0u;
+        gp[e] = (ok && has_post) ? *reinterpret_cast<const uint32_t*>(g_post + k) : 0u;
+        bp[e] = (ok && has_post) ? *reinterpret_cast<const uint32_t*>(b_post + k) : 0u;
+    }
+    pdl_launch_dependents();
+    pdl_wait();
+
+    auto row_reduce = [&](float s, int buf) -> float {   // sum over the row group; one barrier per call
+        s = warp_sum(s);
+        if (lane == 0) red[buf][row][wr] = s;
         __syncthreads();
-        const float r = bcast[row];
-        __syncthreads();
-        return r;
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < WPR; ++i) t += red[buf][row][i];
+        return t;
     };
+    auto lo = [](uint32_t u) { return __uint_as_float(u << 16); };
+    auto hi = [](uint32_t u) { return __uint_as_float(u & 0xffff0000u); };
+
+    float2 v[NP];
     const float inv_k = 1.0f / K;
-    // ---- y = res_in (+ LN_post(gemm_out)) ----
-    if (gemm_out != nullptr) {
+    if (has_post) {
+        uint32_t go[NP];
+        float2 rs[NP];
+#pragma unroll
+        for (int e = 0; e < NP; ++e) {
+            const int k = 2 * (tr + e * TPR);
+            const bool ok = k < K && row_ok;
+            go[e] = ok ? *reinterpret_cast<const uint32_t*>(gemm_out + (size_t)row * K + k) : 0u;
+            rs[e] = ok ? *reinterpret_cast<const float2*>(res_in + (size_t)row * K + k) : make_float2(0.f, 0.f);
+        }
+        const float c = *absmax_gemm * 0.125f;
         float s = 0.f;
 #pragma unroll
-        for (int e = 0; e < MAXE; ++e) {
-            const int k = tr + e * TPR;
-            v[e] = (e < ne && row_ok) ? __bfloat162float(gemm_out[(size_t)row * K + k]) : 0.f;
-            s += v[e];
-        }
-        const float mean = row_sum(s) * inv_k;
+        for (int e = 0; e < NP; ++e) { v[e] = make_float2(lo(go[e]), hi(go[e])); s += v[e].x + v[e].y; }
+        const float mean = row_reduce(s, 0) * inv_k;
         float ss = 0.f;
 #pragma unroll
-        for (int e = 0; e < MAXE; ++e) if (e < ne) { const float d = v[e] - mean; ss += d * d; }
-        const float var = row_sum(ss) * inv_k;
-        const float c = *absmax_gemm * 0.125f;
+        for (int e = 0; e < NP; ++e) {
+            if (2 * (tr + e * TPR) < K) {
+                const float a = v[e].x - mean, b = v[e].y - mean;
+                ss += a * a + b * b;
+            }
+        }
+        const float var = row_reduce(ss, 1) * inv_k;
         const float rstd = rsqrtf(var + eps * c * c);
 #pragma unroll
-        for (int e = 0; e < MAXE; ++e) {
-            const int k = tr + e * TPR;
-            if (e < ne && row_ok)
-                v[e] = (v[e] - mean) * rstd * __bfloat162float(g_post[k]) + __bfloat162float(b_post[k]) +
-                       res_in[(size_t)row * K + k];
+        for (int e = 0; e < NP; ++e) {
+            v[e].x = (v[e].x - mean) * rstd * lo(gp[e]) + lo(bp[e]) + rs[e].x;
+            v[e].y = (v[e].y - mean) * rstd * hi(gp[e]) + hi(bp[e]) + rs[e].y;
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < MAXE; ++e) {
-            const int k = tr + e * TPR;
-            v[e] = (e < ne && row_ok) ? res_in[(size_t)row * K + k] : 0.f;
+        for (int e = 0; e < NP; ++e) {
+            const int k = 2 * (tr + e * TPR);
+            v[e] = (k < K && row_ok) ? *reinterpret_cast<const float2*>(res_in + (size_t)row * K + k)
+                                     : make_float2(0.f, 0.f);
         }
     }
     float mx = 0.f, s = 0.f;
 #pragma unroll
-    for (int e = 0; e < MAXE; ++e) {
-        const int k = tr + e * TPR;
-        if (e < ne && row_ok) {
-            if (res_out != nullptr) res_out[(size_t)row * K + k] = v[e];
-            mx = fmaxf(mx, fabsf(v[e]));
-            s += v[e];
+    for (int e = 0; e < NP; ++e) {
+        const int k = 2 * (tr + e * TPR);
+        if (k < K && row_ok) {
+            if (res_out != nullptr) *reinterpret_cast<float2*>(res_out + (size_t)row * K + k) = v[e];
+            mx = fmaxf(mx, fmaxf(fabsf(v[e].x), fabsf(v[e].y)));
+            s += v[e].x + v[e].y;
         }
     }
-    // ---- max|y| over the whole tensor ----
     mx = warp_max(mx);
-    if (lane == 0) smax[warp] = mx;
+    s = warp_sum(s);
+    if (lane == 0) { smax[warp] = mx; red[2][row][wr] = s; }
     __syncthreads();
     float am = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) am = fmaxf(am, smax[i]);
-    // ---- xn = LN_pre(y) ----
-    const float mean = row_sum(s) * inv_k;
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) tsum += red[2][row][i];
+    const float mean = tsum * inv_k;
     float ss = 0.f;
 #pragma unroll
-    for (int e = 0; e < MAXE; ++e) if (e < ne && row_ok) { const float d = v[e] - mean; ss += d * d; }
-    const float var = row_sum(ss) * inv_k;
+    for (int e = 0; e < NP; ++e) {
+        if (2 * (tr + e * TPR) < K && row_ok) {
+            const float a = v[e].x - mean, b = v[e].y - mean;
+            ss += a * a + b * b;
+        }
+    }
+    const float var = row_reduce(ss, 3) * inv_k;
     const float c = am * 0.125f;
     const float rstd = rsqrtf(var + eps * c * c);
 #pragma unroll
-    for (int e = 0; e < MAXE; ++e) {
-        const int k = tr + e * TPR;
-        if (e < ne && row_ok)
-            xn_out[(size_t)row * K + k] =
-                __float2bfloat16_rn((v[e] - mean) * rstd * __bfloat162float(g_pre[k]) + __bfloat162float(b_pre[k]));
+    for (int e = 0; e < NP; ++e) {
+        const int k = 2 * (tr + e * TPR);
+        if (k < K && row_ok) {
+            const float a = (v[e].x - mean) * rstd * lo(gq[e]) + lo(bq[e]);
+            const float b = (v[e].y - mean) * rstd * hi(gq[e]) + hi(bq[e]);
+            *reinterpret_cast<uint32_t*>(xn_out + (size_t)row * K + k) = pack_bf16x2(a, b);
+        }
     }
 }
 
@@ -269,6 +319,8 @@ attn_decode_kernel(const DecodeParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, sub = lane & 7;
     const int h = p.heads * HD;
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = p.cur_len_dev ? *p.cur_len_dev : p.cur_len;   // cached tokens; the new token sits at index t
     const __nv_bfloat16* qrow = p.qkv + (size_t)batch * 3 * h + head * HD + sub * 8;
     float q[8], kn[8], vn[8];
@@ -349,6 +401,8 @@ attn_decode_kernel(const DecodeParams p) {
 
 __global__ void attn_decode_combine_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out,
                                            int heads, int nsplit) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int head = blockIdx.x, batch = blockIdx.y, d = threadIdx.x;
     const float* src = partial + ((size_t)batch * heads + head) * nsplit * (HD + 2);
     float M = -INFINITY;
@@ -383,10 +437,11 @@ extern "C" int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int6
     // the MMA N dimension holds up to 8 batch rows; 9..16 rows take a second pass over the weights
     for (int m0 = 0; m0 < M; m0 += 8) {
         const int mm = (M - m0) < 8 ? (M - m0) : 8;
-        linear_small_m_kernel<<<grid, SK_WARPS * 32, 0, s>>>(xb + (size_t)m0 * ldx, ldx, wb, ldw, bb,
-                                                            static_cast<char*>(out) + (size_t)m0 * ldo * osz, ldo,
-                                                            out_is_f32, act, absmax, mm, N, K);
-        CV_LAUNCH_CHECK();
+        CV_CUDA(cvh::launch_pdl(linear_small_m_kernel, dim3(grid), dim3(SK_WARPS * 32), 0, s, true,
+                                xb + (size_t)m0 * ldx, ldx, wb, ldw, bb,
+                                static_cast<void*>(static_cast<char*>(out) + (size_t)m0 * ldo * osz), ldo, out_is_f32,
+                                act, absmax, mm, N, K));
+        cvh::count_launches(1);
     }
     return 0;
 }
@@ -396,24 +451,35 @@ extern "C" int cv_ln_pair_small_m(const float* res_in, const void* gemm_out, con
                                   float eps, float* res_out, void* xn_out, int M, int K, void* stream) {
     CV_REQUIRE(res_in && g_pre && b_pre && xn_out, "null pointer");
     CV_REQUIRE(gemm_out == nullptr || (absmax_gemm && g_post && b_post), "gemm_out needs absmax_gemm, g_post, b_post");
-    CV_REQUIRE(M >= 1 && M <= 16 && K > 0, "1 <= M <= 16");
+    CV_REQUIRE(M >= 1 && M <= 16 && K > 0 && K % 2 == 0, "1 <= M <= 16, K even");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const __nv_bfloat16* go = static_cast<const __nv_bfloat16*>(gemm_out);
     const __nv_bfloat16 *gp = static_cast<const __nv_bfloat16*>(g_post), *bp = static_cast<const __nv_bfloat16*>(b_post);
     const __nv_bfloat16 *gq = static_cast<const __nv_bfloat16*>(g_pre), *bq = static_cast<const __nv_bfloat16*>(b_pre);
     __nv_bfloat16* xo = static_cast<__nv_bfloat16*>(xn_out);
-#define LAUNCH(MT)                                                                                              \
-    do {                                                                                                        \
-        CV_REQUIRE(K <= (32 / MT) * 32 * (MT <= 4 ? 16 : (MT == 8 ? 24 : 40)), "K too large for cv_ln_pair_small_m");                   \
-        ln_pair_kernel<MT><<<1, LP_THREADS, 0, s>>>(res_in, go, absmax_gemm, gp, bp, gq, bq, eps, res_out, xo, M, K); \
+    const int MT = M == 1 ? 1 : (M == 2 ? 2 : (M <= 4 ? 4 : (M <= 8 ? 8 : 16)));
+    const int tpr = (32 / MT) * 32;
+    const int need = (K + 2 * tpr - 1) / (2 * tpr);      // bf16 pairs per thread
+    CV_REQUIRE(need <= 40, "K too large for cv_ln_pair_small_m at this M");
+#define LP(MT_, NP_)                                                                                            \
+    CV_CUDA(cvh::launch_pdl(ln_pair_kernel<MT_, NP_>, dim3(1), dim3(LP_THREADS), 0, s, true, res_in, go, absmax_gemm, \
+                            gp, bp, gq, bq, eps, res_out, xo, M, K))
+#define LP_BY_NP(MT_)                                  \
+    do {                                               \
+        if (need <= 2) LP(MT_, 2);                     \
+        else if (need <= 5) LP(MT_, 5);                \
+        else if (need <= 10) LP(MT_, 10);              \
+        else if (need <= 20) LP(MT_, 20);              \
+        else LP(MT_, 40);                              \
     } while (0)
-    if (M == 1) LAUNCH(1);
-    else if (M == 2) LAUNCH(2);
-    else if (M <= 4) LAUNCH(4);
-    else if (M <= 8) LAUNCH(8);
-    else LAUNCH(16);
-#undef LAUNCH
-    CV_LAUNCH_CHECK();
+    if (MT == 1) LP_BY_NP(1);
+    else if (MT == 2) LP_BY_NP(2);
+    else if (MT == 4) LP_BY_NP(4);
+    else if (MT == 8) LP_BY_NP(8);
+    else LP_BY_NP(16);
+#undef LP_BY_NP
+#undef LP
+    cvh::count_launches(1);
     return 0;
 }
 
@@ -441,12 +507,12 @@ extern "C" int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_
     p.heads = heads; p.nsplit = nsplit; p.max_len = max_len;
     p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
     dim3 grid(heads, b, nsplit);
-    attn_decode_kernel<<<grid, DA_WARPS * 32, 0, s>>>(p);
-    CV_LAUNCH_CHECK();
+    CV_CUDA(cvh::launch_pdl(attn_decode_kernel, grid, dim3(DA_WARPS * 32), 0, s, true, p));
+    cvh::count_launches(1);
     if (nsplit > 1) {
-        attn_decode_combine_kernel<<<dim3(heads, b), HD, 0, s>>>(workspace, static_cast<__nv_bfloat16*>(out), heads,
-                                                                nsplit);
-        CV_LAUNCH_CHECK();
+        CV_CUDA(cvh::launch_pdl(attn_decode_combine_kernel, dim3(heads, b), dim3(HD), 0, s, true,
+                                static_cast<const float*>(workspace), static_cast<__nv_bfloat16*>(out), heads, nsplit));
+        cvh::count_launches(1);
     }
     return 0;
 }

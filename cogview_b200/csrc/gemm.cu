@@ -309,14 +309,16 @@ extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
 
     int BN = block_n;
     if (BN == 0) {
-        // fewest (waves x tile width) on the SM count; ties go to the wider tile
+        // Estimated time = waves x per-tile cost.  A 128x128 tile needs as many shared-memory operand bytes per
+        // MMA cycle as the SM can deliver (128 B/clk), so it runs at ~2/3 of the 128x256 tile's per-column rate
+        // (measured: ~0.9 vs ~1.4 PFLOP/s): cost 192 vs 256 per tile.
         const int sms = cvh::num_sms();
         const int mb = (M + BM - 1) / BM;
-        auto cost = [&](int bn) {
+        auto waves = [&](int bn) {
             long tiles = (long)mb * ((N + bn - 1) / bn);
-            return ((tiles + sms - 1) / sms) * bn;
+            return (tiles + sms - 1) / sms;
         };
-        BN = (cost(128) < cost(256)) ? 128 : 256;
+        BN = (waves(128) * 192 < waves(256) * 256) ? 128 : 256;
     }
     CV_REQUIRE(BN == 128 || BN == 256, "block_n must be 0 (auto), 128 or 256");
 

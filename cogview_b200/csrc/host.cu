@@ -1,5 +1,7 @@
 #include "host.h"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -28,6 +30,15 @@ int fail_cu(const char* fn, CUresult r) {
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("COGVIEW_B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 
 int num_sms() {
     static int n = 0;

@@ -37,6 +37,26 @@ int num_sms();
 void count_launches(int n);
 long long launches();   // kernels launched by this library since load (cv_launch_count)
 
+// Launch with programmatic dependent launch (PDL) allowed: the kernel may become resident while the previous
+// kernel in the stream drains.  Such kernels call cv::pdl_wait() before touching anything the previous kernel
+// wrote.  COGVIEW_B200_PDL=0 disables the attribute (plain stream order).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                       Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 enum class Swizzle { None, B128 };
 
 // Encode a tiled tensor map.  dims/strides are innermost-first, strides in BYTES for dims 1..rank-1.

@@ -16,6 +16,7 @@ using namespace cv;
 __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos,
                                  const __nv_bfloat16* __restrict__ wte, const __nv_bfloat16* __restrict__ wpe,
                                  float* __restrict__ out, float* __restrict__ absmax, int rows, int h) {
+    pdl_launch_dependents();   // lets a PDL-launched consumer (decode path) start its prologue early
     const int warps_per_block = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float mx = 0.f;
