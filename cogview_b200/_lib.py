@@ -42,6 +42,13 @@ def _declare(lib):
         "cv_adamw_step": [P, P, P, P, P, L, F, F, F, F, F, I, P, F, P],
         "cv_sumsq_bf16": [P, L, P, P],
         "cv_clip_coef": [P, F, P, P, P],
+        "cv_conv2d_k4s2": [P, P, P, P, I, I, I, I, I, I, P],
+        "cv_conv_transpose2d_k4s2": [P, P, P, P, I, I, I, I, I, I, P],
+        "cv_im2col_k4s2_c3": [P, P, I, I, I, P],
+        "cv_vq_split3": [P, P, L, I, P],
+        "cv_vq_argmin": [P, L, P, P, P, P, L, I, I, F, P],
+        "cv_vq_lookup": [P, P, P, P, L, I, P],
+        "cv_conv1x1_out3": [P, P, P, P, P, P, I, I, I, I, P],
         "cv_embed_fwd": [P, P, P, P, P, P, I, I, P],
         "cv_embed_bwd": [P, P, P, P, P, I, I, P],
         "cv_cross_entropy_fwd": [P, L, P, P, P, P, I, I, P],

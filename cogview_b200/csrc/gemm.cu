@@ -38,7 +38,7 @@ struct GemmParams {
     int M, N, K;
     int num_m_blocks, num_n_blocks, num_k_blocks;
     const __nv_bfloat16* bias;  // [N] or null
-    int act;                    // 0 none, 1 tanh-GELU
+    int act;                    // 0 none, 1 tanh-GELU, 2 ReLU
     float* absmax;              // null or scalar: atomicMax |C| over valid entries
     int has_c2;                 // second bf16 output = pre-activation (bias added, no GELU)
 };
@@ -200,6 +200,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (!is_pre && p.act == 1) {
 #pragma unroll
                         for (int j = 0; j < EPI_COLS; ++j) v[j] = gelu_tanh(v[j]);
+                    } else if (!is_pre && p.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < EPI_COLS; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
                     uint8_t* buf = epi_buf + (buf_sel & 1) * EPI_BYTES;
                     if (epi_tid == 0) tma_store_wait_read<1>();  // the store that last read `buf` has drained
@@ -303,7 +306,7 @@ extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     CV_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(Cout) & 15) == 0,
                "operands must be 16-byte aligned");
-    CV_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (tanh-GELU)");
+    CV_REQUIRE(act >= 0 && act <= 2, "act must be 0 (none), 1 (tanh-GELU) or 2 (ReLU)");
     CV_REQUIRE(!(C2 && c_is_f32), "pre-activation output requires bf16 C");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 

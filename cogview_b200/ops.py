@@ -10,6 +10,7 @@ from ._lib import check, lib, ptr, require_cuda, stream_ptr
 
 ACT_NONE = 0
 ACT_GELU = 1
+ACT_RELU = 2
 
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, bias=None, act=ACT_NONE, out_dtype=torch.bfloat16,
@@ -259,3 +260,80 @@ def ln_pair_small_m(res_in, gemm_out, absmax_gemm, post, pre, eps, *, want_res_o
                                   ptr(pre[1]), float(eps), ptr(y), ptr(xn), M, K, stream_ptr())
     check(rc, "cv_ln_pair_small_m")
     return y, xn
+
+
+# ----------------------------------------------------------------------------------------------------
+# VQ-VAE kernels (NHWC bf16 activations)
+# ----------------------------------------------------------------------------------------------------
+def conv2d_k4s2(x, w_packed, bias, relu):
+    """x: [B, H, W, Cin] bf16 NHWC; w_packed: [16, Cout, Cin] bf16 -> [B, H/2, W/2, Cout] bf16."""
+    require_cuda(x, w_packed, bias)
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[1]
+    assert x.is_contiguous() and w_packed.is_contiguous() and x.dtype == torch.bfloat16
+    y = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device)
+    check(lib().cv_conv2d_k4s2(ptr(x), ptr(w_packed), ptr(bias), ptr(y), B, H, W, Cin, Cout, int(relu), stream_ptr()),
+          "cv_conv2d_k4s2")
+    return y
+
+
+def conv_transpose2d_k4s2(x, w_packed, bias, relu):
+    """x: [B, H, W, Cin] bf16 NHWC; w_packed: [16, Cout, Cin] bf16 -> [B, 2H, 2W, Cout] bf16."""
+    require_cuda(x, w_packed, bias)
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[1]
+    assert x.is_contiguous() and w_packed.is_contiguous() and x.dtype == torch.bfloat16
+    y = torch.empty((B, 2 * H, 2 * W, Cout), dtype=torch.bfloat16, device=x.device)
+    check(lib().cv_conv_transpose2d_k4s2(ptr(x), ptr(w_packed), ptr(bias), ptr(y), B, H, W, Cin, Cout, int(relu),
+                                         stream_ptr()), "cv_conv_transpose2d_k4s2")
+    return y
+
+
+def im2col_k4s2_c3(img):
+    """img: [B, 3, H, W] fp32 NCHW -> [B*(H/2)*(W/2), 64] bf16 patches (48 used)."""
+    require_cuda(img)
+    B, C, H, W = img.shape
+    assert C == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    out = torch.empty((B * (H // 2) * (W // 2), 64), dtype=torch.bfloat16, device=img.device)
+    check(lib().cv_im2col_k4s2_c3(ptr(img), ptr(out), B, H, W, stream_ptr()), "cv_im2col_k4s2_c3")
+    return out
+
+
+def vq_split3(z):
+    require_cuda(z)
+    rows, dim = z.shape
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    out = torch.empty((rows, 3 * dim), dtype=torch.bfloat16, device=z.device)
+    check(lib().cv_vq_split3(ptr(z), ptr(out), rows, dim, stream_ptr()), "cv_vq_split3")
+    return out
+
+
+def vq_argmin(scores, e2, z, codebook, margin=1e-4):
+    require_cuda(scores, e2, z, codebook)
+    rows, n_embed = scores.shape
+    assert scores.dtype == torch.float32 and scores.stride(1) == 1 and codebook.is_contiguous() and z.is_contiguous()
+    idx = torch.empty(rows, dtype=torch.int64, device=scores.device)
+    check(lib().cv_vq_argmin(ptr(scores), scores.stride(0), ptr(e2), ptr(z), ptr(codebook), ptr(idx), rows, n_embed,
+                             codebook.shape[1], float(margin), stream_ptr()), "cv_vq_argmin")
+    return idx
+
+
+def vq_lookup(idx, codebook, want_bf16=True, want_f32=False):
+    require_cuda(idx, codebook)
+    idx = idx.contiguous().view(-1)
+    rows, dim = idx.numel(), codebook.shape[1]
+    ob = torch.empty((rows, dim), dtype=torch.bfloat16, device=idx.device) if want_bf16 else None
+    of = torch.empty((rows, dim), dtype=torch.float32, device=idx.device) if want_f32 else None
+    check(lib().cv_vq_lookup(ptr(idx), ptr(codebook), ptr(ob), ptr(of), rows, dim, stream_ptr()), "cv_vq_lookup")
+    return ob, of
+
+
+def conv1x1_out3(x, w, bias, scale, shift):
+    """x: [B, H, W, Cin] bf16 NHWC; w: [3, Cin] fp32 -> [B, 3, H, W] fp32 = (x.w + bias) * scale + shift."""
+    require_cuda(x, w, bias, scale, shift)
+    B, H, W, Cin = x.shape
+    assert x.is_contiguous() and w.is_contiguous() and w.dtype == torch.float32
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+    check(lib().cv_conv1x1_out3(ptr(x), ptr(w), ptr(bias), ptr(scale), ptr(shift), ptr(out), B, H, W, Cin,
+                                stream_ptr()), "cv_conv1x1_out3")
+    return out

@@ -1,0 +1,1 @@
+from .api import code2img, img2code, new_model  # noqa: F401

@@ -149,6 +149,34 @@ int cv_adamw_step(void* param, const void* grad, float* master, float* m, float*
 int cv_sumsq_bf16(const void* x, int64_t n, float* out, void* stream);   /* *out += sum(x^2) */
 int cv_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * VQ-VAE image tokenizer (vqvae/vqvae_zc.py, vqvae/api.py), NHWC bf16 activations.
+ *   cv_conv2d_k4s2 / cv_conv_transpose2d_k4s2: nn.Conv2d / nn.ConvTranspose2d (kernel 4, stride 2, padding 1) of
+ *     Encoder (vqvae_zc.py:121-129) and Decoder (:172-191) as im2col-free implicit GEMMs on tcgen05: A tiles are
+ *     TMA boxes of the NHWC input (traversal stride 2 / sub-pixel phases, zero-filled halo = padding).
+ *     x: [B, IH, IW, Cin]; w_packed: [16 (ky*4+kx), Cout, Cin] bf16; bias bf16 [Cout] or NULL; relu fused.
+ *     y: [B, IH/2, IW/2, Cout] (conv) or [B, 2IH, 2IW, Cout] (transposed).  Cin % 64 == 0, Cout % 128 == 0,
+ *     tile-grid H, W powers of two with W <= 128.
+ *   cv_im2col_k4s2_c3: patches of the fp32 NCHW 3-channel image -> [B*OH*OW, 64] bf16 (48 used) for the first conv
+ *     (run as cv_gemm_bf16 with act = 2).
+ *   cv_vq_split3 / cv_vq_argmin / cv_vq_lookup: Quantize.forward_ hard path (vqvae_zc.py:41-54) and embed_code (:95-96);
+ *     scores = split3(z) . [E_hi|E_lo|E_hi]^T via cv_gemm_bf16 (fp32 out); argmin of e2[j] - 2 scores[j] with exact
+ *     fp32 re-scoring of the two best codes when closer than `margin` (relative); ties -> lowest index.
+ *   cv_conv1x1_out3: Decoder's final 1x1 conv to 3 channels (:191) + de-normalisation of vqvae/api.py:43, NCHW fp32 out.
+ * ---------------------------------------------------------------------------------------------- */
+int cv_conv2d_k4s2(const void* x, const void* w_packed, const void* bias, void* y, int B, int IH, int IW, int Cin,
+                   int Cout, int relu, void* stream);
+int cv_conv_transpose2d_k4s2(const void* x, const void* w_packed, const void* bias, void* y, int B, int IH, int IW,
+                             int Cin, int Cout, int relu, void* stream);
+int cv_im2col_k4s2_c3(const float* img, void* out, int B, int H, int W, void* stream);
+int cv_vq_split3(const float* z, void* out, int64_t rows, int dim, void* stream);
+int cv_vq_argmin(const float* scores, int64_t ld, const float* e2, const float* z, const float* codebook,
+                 int64_t* idx_out, int64_t rows, int n_embed, int dim, float margin, void* stream);
+int cv_vq_lookup(const int64_t* idx, const float* codebook, void* out_bf16, float* out_f32, int64_t rows, int dim,
+                 void* stream);
+int cv_conv1x1_out3(const void* x, const float* w, const float* bias, const float* scale, const float* shift,
+                    float* out, int B, int H, int W, int cin, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
