@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="both", choices=["sample", "train", "both"])
+    ap.add_argument("--workload", default="all", choices=["sample", "train", "vqvae", "both", "all"])
+    ap.add_argument("--vq-batch", type=int, default=256)
     ap.add_argument("--batch", type=int, default=4, help="beams per GPU (sampling) / sequences per GPU (training)")
     ap.add_argument("--gen-tokens", type=int, default=1024)
     ap.add_argument("--model", default="4b", choices=["4b", "tiny"])
@@ -371,6 +372,75 @@ def gemm_roofline(cfg, M):
 
 
 # ----------------------------------------------------------------------------------------------------
+# VQ-VAE tokenizer workload (configs[3]): encode + quantise + decode of 256x256 images
+# ----------------------------------------------------------------------------------------------------
+def run_vqvae(args, world, rank, dev_index, steps, warmup):
+    from cogview_b200 import vqvae
+    from oracle import recipes
+    model = vqvae.new_model()
+    model.load_state_dict(recipes.vqvae_state_dict(seed=0))
+    model = model.cuda().eval()
+    B = args.vq_batch
+    g = torch.Generator().manual_seed(rank)
+    host_img = torch.randn((B, 3, 256, 256), generator=g).pin_memory()
+    dev_img = host_img.cuda()
+    host_out = torch.empty((B, 3, 256, 256)).pin_memory()
+    keep = {}
+
+    def step_dev():
+        codes = vqvae.img2code(model, dev_img)
+        keep["codes"] = codes
+        keep["rec"] = vqvae.code2img(model, codes.view(B, 32, 32))
+
+    def step_e2e():
+        img = host_img.cuda(non_blocking=True)
+        codes = vqvae.img2code(model, img)
+        rec = vqvae.code2img(model, codes.view(B, 32, 32))
+        host_out.copy_(rec, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    l0 = launches()
+    ms_dev, clocks = timed(step_dev, steps, warmup, dev_index)
+    n_launch = launches() - l0
+    ms_e2e, _ = timed(step_e2e, steps, 1, dev_index)
+    assert keep["codes"].shape == (B, 1024) and int(keep["codes"].max()) < 8192
+    assert bool(torch.isfinite(keep["rec"]).all())
+    imgs = B * world
+    gflop_per_image = 44.0 + 4.29 + 176.3            # encoder + distance + decoder
+    pk = peaks()
+    achieved = gflop_per_image * imgs / world / (ms_dev / steps / 1e3) / 1e3
+    res = dict(value=imgs * steps / (ms_dev / 1e3), unit="images/s", code_tokens_per_s=imgs * 1024 * steps / (ms_dev / 1e3),
+               ms_per_step=ms_dev / steps, steps=steps, warmup=warmup, clocks=clocks,
+               e2e=dict(value=imgs * steps / (ms_e2e / 1e3), unit="images/s",
+                        h2d_bytes_per_step=int(host_img.numel() * 4), d2h_bytes_per_step=int(host_out.numel() * 4)),
+               gpu_launches=int(n_launch / max(1, steps + warmup)) * steps,
+               config=dict(workload="configs[3]: VQ-VAE (new_model(): 512 ch, 8192 codes) img2code + code2img, %d "
+                                    "synthetic 256x256 images per GPU, bf16 tensor-core convs, fp32-rescored arg-min" % B,
+                           parallelism="dp%d (independent images per rank, no collective)" % world),
+               roofline_step=dict(bound="tensor", achieved=achieved, peak=pk["tf_sust"], unit="TFLOP/s",
+                                  frac=achieved / pk["tf_sust"], peak_source=pk["src"],
+                                  note="whole round trip (224.6 GFLOP/image algorithmic) vs sustained cuBLAS bf16 peak"))
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_baseline_vqvae(nimg=4):
+    from oracle import cogview_oracle as O
+    from oracle import recipes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = recipes.vqvae_state_dict(seed=0)
+    img = recipes.images(nimg, size=256, seed=1)
+    t0 = time.perf_counter()
+    codes = O.img2code(sd, img)
+    O.code2img(sd, codes.view(nimg, 32, 32))
+    dt = time.perf_counter() - t0
+    return dict(value=nimg / dt, unit="images/s", cores=cores, kind="port",
+                sample="oracle port, fp32, %d threads: img2code + code2img of %d 256x256 images (%.1f s)" % (cores, nimg, dt))
+
+
+# ----------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference path on the host cores
 # ----------------------------------------------------------------------------------------------------
 def cpu_baseline_sample(cfg, nb, gen_tokens, budget_s=20.0):
@@ -476,7 +546,7 @@ def main():
                     dtype="f32", cpu_baseline=cb, config=dict(workload=workload_name, parallelism="cpu"),
                     e2e=dict(value=cb["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0, wall_s=time.perf_counter() - t0)
-        if args.workload in ("train", "both"):
+        if args.workload in ("train", "both", "all"):
             line["train"] = dict(cpu_baseline=cpu_baseline_train(cfg))
             line["train"]["value"] = line["train"]["cpu_baseline"]["value"]
         print(json.dumps(line))
@@ -493,14 +563,21 @@ def main():
         mpu.initialize_model_parallel(1)
 
     line = dict(base)
-    if args.workload in ("sample", "both"):
+    if args.workload in ("sample", "both", "all"):
         r = run_sample(args, cfg, world, rank, local_rank)
         line.update(value=r["value"], ms_per_step=r["ms_per_step"], e2e=r["e2e"], clocks=r["clocks"],
                     gpu_launches=r["gpu_launches"], roofline=r["roofline"],
                     config=dict(workload=workload_name, global_batch=args.batch * world, seq_len=1089,
                                 parallelism="dp%d (independent sequences per rank, no collective)" % world,
                                 l2="each decode step streams 7.9 GB of weights (>> 126 MB L2)", params=r["params"]))
-    if args.workload in ("train", "both"):
+    if args.workload in ("vqvae", "all"):
+        v = run_vqvae(args, world, rank, local_rank, max(3, args.steps), max(3, args.warmup))
+        if args.workload == "vqvae":
+            line.update(metric="images/sec (VQ-VAE encode+quantise+decode, 256x256)", unit="images/s", value=v["value"],
+                        ms_per_step=v["ms_per_step"], e2e=v["e2e"], clocks=v["clocks"], gpu_launches=v["gpu_launches"],
+                        roofline=v["roofline_step"], config=v["config"], steps=v["steps"], warmup=v["warmup"])
+        line["vqvae"] = v
+    if args.workload in ("train", "both", "all"):
         tsteps = args.train_steps or max(3, args.steps)
         t = run_train(args, cfg, world, rank, local_rank, tsteps, max(3, args.warmup))
         if args.workload == "train":
@@ -509,9 +586,13 @@ def main():
                         config=t["config"], steps=t["steps"], warmup=t["warmup"])
         line["train"] = t
     if rank == 0:
-        if args.workload in ("sample", "both"):
+        if args.workload in ("sample", "both", "all"):
             line["cpu_baseline"] = cpu_baseline_sample(cfg, args.batch, args.gen_tokens)
-        if args.workload in ("train", "both"):
+        if args.workload in ("vqvae", "all"):
+            line["vqvae"]["cpu_baseline"] = cpu_baseline_vqvae()
+            if args.workload == "vqvae":
+                line["cpu_baseline"] = line["vqvae"]["cpu_baseline"]
+        if args.workload in ("train", "both", "all"):
             line["train"]["cpu_baseline"] = cpu_baseline_train(cfg)
             if args.workload == "train":
                 line["cpu_baseline"] = line["train"]["cpu_baseline"]
