@@ -11,7 +11,7 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles -> 128B-swizzled smem ring (4-6 stages)
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM;
 //               two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps tile i+1
-//   warps 2-5   epilogue: tcgen05.ld -> bias/GELU/abs-max -> swizzled smem staging -> TMA store
+//   warps 2-5   epilogue: tcgen05.ld -> bias/GELU/abs-max -> each thread stores its row's 128 B straight to global
 #include "common.cuh"
 #include "host.h"
 #include "../../include/cogview_b200.h"
@@ -23,7 +23,6 @@ using namespace cv;
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_BYTES = 128 * 128;  // 128 rows x 128 bytes
 
 template <int BN>
 struct Cfg {
@@ -31,7 +30,7 @@ struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -40,18 +39,19 @@ struct GemmParams {
     const __nv_bfloat16* bias;  // [N] or null
     int act;                    // 0 none, 1 tanh-GELU, 2 ReLU
     float* absmax;              // null or scalar: atomicMax |C| over valid entries
-    int has_c2;                 // second bf16 output = pre-activation (bias added, no GELU)
+    int has_c2;                 // second bf16 output = pre-activation (bias added, no activation)
+    void* c;                    // output [M, N] (bf16 or fp32), leading dimension ldc
+    __nv_bfloat16* c2;          // optional pre-activation output (bf16, same ldc)
+    int64_t ldc;
 };
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi_buf = smem + C::STAGES * C::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + 2 * EPI_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t* full_bar = bars;                       // [STAGES]
     uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
     uint64_t* tmem_full = bars + 2 * C::STAGES;      // [2]
@@ -65,7 +65,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        tma_prefetch_desc(&tmC);
         for (int i = 0; i < C::STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -149,13 +148,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else {
         // ------------------------------ epilogue warps ------------------------------
+        // Each thread owns one accumulator row: it reads 64 (bf16 out) or 32 (fp32 out) columns from TMEM, applies
+        // bias / activation / abs-max and writes its 128 contiguous bytes of C straight to global memory (whole
+        // cache lines per thread) — no staging buffer, no barriers: the four warps run fully decoupled, so the
+        // epilogue of tile i stays hidden under the MMAs of tile i+1.
         const int q = warp_idx & 3;             // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;          // row within the tile
-        const int epi_tid = threadIdx.x - 64;   // 0..127
         constexpr int EPI_COLS = OUT_F32 ? 32 : 64;
         constexpr int NCHUNK = BN / EPI_COLS;
+        const bool n_vec_ok = (p.N % 8) == 0;   // whole 16-byte groups are either inside or outside [0, N)
         int it = 0;
-        uint32_t buf_sel = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m0 = (tile % p.num_m_blocks) * BM;
             const int n0 = (tile / p.num_m_blocks) * BN;
@@ -163,7 +165,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            const bool row_ok = (m0 + row) < p.M;
+            const int grow = m0 + row;
+            const bool row_ok = grow < p.M;
             float tmax = 0.f;
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
@@ -186,62 +189,92 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int ncol0 = n0 + c * EPI_COLS;
                 float v[EPI_COLS];
 #pragma unroll
-                for (int j = 0; j < EPI_COLS; ++j) {
-                    float x = __uint_as_float(r[j]);
-                    if (p.bias != nullptr) {
-                        const int n = ncol0 + j;
-                        x += (n < p.N) ? __bfloat162float(p.bias[n]) : 0.f;
-                    }
-                    v[j] = x;
-                }
-                const int rounds = p.has_c2 ? 2 : 1;
-                for (int round = 0; round < rounds; ++round) {
-                    const bool is_pre = p.has_c2 && round == 0;
-                    if (!is_pre && p.act == 1) {
+                for (int j = 0; j < EPI_COLS; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < EPI_COLS; ++j) v[j] = gelu_tanh(v[j]);
-                    } else if (!is_pre && p.act == 2) {
+                    for (int g = 0; g < EPI_COLS / 8; ++g) {
+                        const int n = ncol0 + g * 8;
+                        if (n_vec_ok && n + 8 <= p.N) {       // one broadcast 16-byte load per 8 columns
+                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+                            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                        for (int j = 0; j < EPI_COLS; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-                    uint8_t* buf = epi_buf + (buf_sel & 1) * EPI_BYTES;
-                    if (epi_tid == 0) tma_store_wait_read<1>();  // the store that last read `buf` has drained
-                    named_bar_sync(1, 128);
-                    uint8_t* rowp = buf + row * 128;
-                    if (OUT_F32) {
+                            for (int t = 0; t < 4; ++t) {
+                                v[g * 8 + 2 * t] += __low2float(b2[t]);
+                                v[g * 8 + 2 * t + 1] += __high2float(b2[t]);
+                            }
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            *reinterpret_cast<float4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+                            for (int t = 0; t < 8; ++t)
+                                if (n + t < p.N) v[g * 8 + t] += __bfloat162float(p.bias[n + t]);
                         }
-                        if (!is_pre && p.absmax != nullptr && row_ok) {
+                    }
+                }
+                if (p.has_c2 && row_ok) {   // pre-activation copy (bf16)
+                    __nv_bfloat16* dst = p.c2 + (size_t)grow * p.ldc + ncol0;
+#pragma unroll
+                    for (int g = 0; g < EPI_COLS / 8; ++g) {
+                        const int n = ncol0 + g * 8;
+                        if (n_vec_ok && n + 8 <= p.N) {
+                            uint4 o;
+                            o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                            o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                            *reinterpret_cast<uint4*>(dst + g * 8) = o;
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t)
+                                if (n + t < p.N) dst[g * 8 + t] = __float2bfloat16_rn(v[8 * g + t]);
+                        }
+                    }
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < EPI_COLS; ++j) v[j] = gelu_tanh_fast(v[j]);
+                } else if (p.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < EPI_COLS; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (row_ok) {
+                    if (OUT_F32) {
+                        float* dst = static_cast<float*>(p.c) + (size_t)grow * p.ldc + ncol0;
+#pragma unroll
+                        for (int g = 0; g < EPI_COLS / 4; ++g) {
+                            const int n = ncol0 + g * 4;
+                            if ((p.N % 4) == 0 && n + 4 <= p.N) {
+                                *reinterpret_cast<float4*>(dst + g * 4) =
+                                    make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    if (n + t < p.N) dst[g * 4 + t] = v[4 * g + t];
+                            }
+                        }
+                        if (p.absmax != nullptr) {
 #pragma unroll
                             for (int j = 0; j < EPI_COLS; ++j)
                                 if (ncol0 + j < p.N) tmax = fmaxf(tmax, fabsf(v[j]));
                         }
                     } else {
+                        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.c) + (size_t)grow * p.ldc + ncol0;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            uint4 o;
-                            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+                        for (int g = 0; g < EPI_COLS / 8; ++g) {
+                            const int n = ncol0 + g * 8;
+                            if (n_vec_ok && n + 8 <= p.N) {
+                                uint4 o;
+                                o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                                o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                                *reinterpret_cast<uint4*>(dst + g * 8) = o;
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 8; ++t)
+                                    if (n + t < p.N) dst[g * 8 + t] = __float2bfloat16_rn(v[8 * g + t]);
+                            }
                         }
-                        if (!is_pre && p.absmax != nullptr && row_ok) {
+                        if (p.absmax != nullptr) {
 #pragma unroll
                             for (int j = 0; j < EPI_COLS; ++j)
                                 if (ncol0 + j < p.N) tmax = fmaxf(tmax, fabsf(bf16_round(v[j])));
                         }
                     }
-                    fence_proxy_async_smem();
-                    named_bar_sync(2, 128);
-                    if (epi_tid == 0) {
-                        tma_store_2d(is_pre ? &tmC2 : &tmC, buf, ncol0, m0);
-                        tma_store_commit();
-                    }
-                    ++buf_sel;
                 }
             }
             if (p.absmax != nullptr) {
@@ -249,7 +282,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (lane == 0 && tmax > 0.f) atomic_max_nonneg(p.absmax, tmax);
             }
         }
-        if (epi_tid == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -261,8 +293,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
-           const GemmParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -272,7 +303,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     }
     int tiles = p.num_m_blocks * p.num_n_blocks;
     int grid = tiles < cvh::num_sms() ? tiles : cvh::num_sms();
-    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cvh::fail_cuda("cv_gemm_bf16", e);
     cvh::count_launches(1);
@@ -280,17 +311,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
 }
 
 template <int BN>
-int dispatch(int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-             const CUtensorMap& tmC2, const GemmParams& p, cudaStream_t s) {
+int dispatch(int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+             cudaStream_t s) {
     if (out_f32) {
-        if (!a_mn && !b_mn) return launch<BN, false, false, true>(tmA, tmB, tmC, tmC2, p, s);
-        if (!a_mn && b_mn) return launch<BN, false, true, true>(tmA, tmB, tmC, tmC2, p, s);
-        if (a_mn && b_mn) return launch<BN, true, true, true>(tmA, tmB, tmC, tmC2, p, s);
+        if (!a_mn && !b_mn) return launch<BN, false, false, true>(tmA, tmB, p, s);
+        if (!a_mn && b_mn) return launch<BN, false, true, true>(tmA, tmB, p, s);
+        if (a_mn && b_mn) return launch<BN, true, true, true>(tmA, tmB, p, s);
         return cvh::fail_arg("cv_gemm_bf16", "A MN-major with B K-major is not instantiated");
     }
-    if (!a_mn && !b_mn) return launch<BN, false, false, false>(tmA, tmB, tmC, tmC2, p, s);
-    if (!a_mn && b_mn) return launch<BN, false, true, false>(tmA, tmB, tmC, tmC2, p, s);
-    if (a_mn && b_mn) return launch<BN, true, true, false>(tmA, tmB, tmC, tmC2, p, s);
+    if (!a_mn && !b_mn) return launch<BN, false, false, false>(tmA, tmB, p, s);
+    if (!a_mn && b_mn) return launch<BN, false, true, false>(tmA, tmB, p, s);
+    if (a_mn && b_mn) return launch<BN, true, true, false>(tmA, tmB, p, s);
     return cvh::fail_arg("cv_gemm_bf16", "A MN-major with B K-major is not instantiated");
 }
 
@@ -334,8 +365,11 @@ extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     p.act = act;
     p.absmax = absmax;
     p.has_c2 = C2 != nullptr;
+    p.c = Cout;
+    p.c2 = static_cast<__nv_bfloat16*>(C2);
+    p.ldc = ldc;
 
-    alignas(64) CUtensorMap tmA, tmB, tmC, tmC2;
+    alignas(64) CUtensorMap tmA, tmB;
     int rc;
     // K-major: stored [rows = M or N, cols = K], box [tile rows x 64]. MN-major: stored [K, M or N], box [64 x 64].
     rc = a_mn_major ? cvh::encode_tmap_2d_bf16(&tmA, A, K, M, lda, BK, 64)
@@ -344,15 +378,6 @@ extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     rc = b_mn_major ? cvh::encode_tmap_2d_bf16(&tmB, B, K, N, ldb, BK, 64)
                     : cvh::encode_tmap_2d_bf16(&tmB, B, N, K, ldb, BN, BK);
     if (rc) return rc;
-    rc = c_is_f32 ? cvh::encode_tmap_2d_f32(&tmC, Cout, M, N, ldc, BM, 32)
-                  : cvh::encode_tmap_2d_bf16(&tmC, Cout, M, N, ldc, BM, 64);
-    if (rc) return rc;
-    if (C2) {
-        rc = cvh::encode_tmap_2d_bf16(&tmC2, C2, M, N, ldc, BM, 64);
-        if (rc) return rc;
-    } else {
-        tmC2 = tmC;
-    }
-    if (BN == 256) return dispatch<256>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, tmC, tmC2, p, s);
-    return dispatch<128>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, tmC, tmC2, p, s);
+    if (BN == 256) return dispatch<256>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, p, s);
+    return dispatch<128>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, p, s);
 }
