@@ -73,7 +73,8 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
     float x2 = x * x;
     float u = 0.7978845608028654f * x * (1.0f + 0.044715f * x2);
-    float t = 1.0f - 2.0f / (__expf(2.0f * u) + 1.0f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
     float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x2);
     return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }

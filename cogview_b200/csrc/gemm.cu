@@ -37,7 +37,8 @@ struct GemmParams {
     int M, N, K;
     int num_m_blocks, num_n_blocks, num_k_blocks;
     const __nv_bfloat16* bias;  // [N] or null
-    int act;                    // 0 none, 1 tanh-GELU, 2 ReLU
+    int act;                    // 0 none, 1 tanh-GELU, 2 ReLU, 3 multiply by gelu'(aux) (GELU backward fused in dgrad)
+    const __nv_bfloat16* aux;   // act == 3: pre-activation values [M, N] (leading dimension ldc)
     float* absmax;              // null or scalar: atomicMax |C| over valid entries
     int has_c2;                 // second bf16 output = pre-activation (bias added, no activation)
     void* c;                    // output [M, N] (bf16 or fp32), leading dimension ldc
@@ -232,6 +233,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 } else if (p.act == 2) {
 #pragma unroll
                     for (int j = 0; j < EPI_COLS; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (p.act == 3 && row_ok) {
+                    const __nv_bfloat16* ax = p.aux + (size_t)grow * p.ldc + ncol0;
+#pragma unroll
+                    for (int g = 0; g < EPI_COLS / 8; ++g) {
+                        const int n = ncol0 + g * 8;
+                        if (n_vec_ok && n + 8 <= p.N) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(ax + g * 8);
+                            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                v[g * 8 + 2 * t] *= gelu_tanh_grad(__low2float(a2[t]));
+                                v[g * 8 + 2 * t + 1] *= gelu_tanh_grad(__high2float(a2[t]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t)
+                                if (n + t < p.N) v[g * 8 + t] *= gelu_tanh_grad(__bfloat162float(ax[g * 8 + t]));
+                        }
+                    }
                 }
                 if (row_ok) {
                     if (OUT_F32) {
@@ -337,7 +357,8 @@ extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     CV_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(Cout) & 15) == 0,
                "operands must be 16-byte aligned");
-    CV_REQUIRE(act >= 0 && act <= 2, "act must be 0 (none), 1 (tanh-GELU) or 2 (ReLU)");
+    CV_REQUIRE(act >= 0 && act <= 3, "act must be 0 (none), 1 (tanh-GELU), 2 (ReLU) or 3 (x gelu'(aux))");
+    CV_REQUIRE(act != 3 || (C2 != nullptr && !c_is_f32), "act 3 takes the pre-activation tensor through C2 (bf16 C)");
     CV_REQUIRE(!(C2 && c_is_f32), "pre-activation output requires bf16 C");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 
@@ -364,7 +385,8 @@ extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     p.bias = static_cast<const __nv_bfloat16*>(bias);
     p.act = act;
     p.absmax = absmax;
-    p.has_c2 = C2 != nullptr;
+    p.has_c2 = C2 != nullptr && act != 3;
+    p.aux = act == 3 ? static_cast<const __nv_bfloat16*>(C2) : nullptr;
     p.c = Cout;
     p.c2 = static_cast<__nv_bfloat16*>(C2);
     p.ldc = ldc;

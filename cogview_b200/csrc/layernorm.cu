@@ -147,6 +147,91 @@ ln_bwd_dx_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const fl
     }
 }
 
+// Fused backward (cols % 256 == 0): the CTA has cols/8 threads, each owning 8 fixed columns (two float4 groups), so
+// its share of dgamma / dbeta lives in 16 registers for the whole kernel and the parameter gradients cost no extra
+// pass.  Rows are processed 4 at a time: one block reduction (8 values) per 4 rows, every operand read exactly once.
+constexpr int FB_R = 4;
+template <typename TIn, typename TDy, typename TDx>
+__global__ void __launch_bounds__(512)
+ln_bwd_fused_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const float* __restrict__ mean_in,
+                    const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ gamma,
+                    const float* __restrict__ dres, TDx* __restrict__ dx, float* __restrict__ partials, int rows,
+                    int cols, int rows_per_cta) {
+    __shared__ float red[2][16][2 * FB_R];          // [buffer][warp][s1 x R, s2 x R]
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = threadIdx.x * 4, c1 = c0 + cols / 2;
+    const float4 g0 = ld4(gamma + c0), g1 = ld4(gamma + c1);
+    float4 dg0 = make_float4(0.f, 0.f, 0.f, 0.f), dg1 = dg0, db0 = dg0, db1 = dg0;
+    const float inv_n = 1.0f / cols;
+    const int r_begin = blockIdx.x * rows_per_cta;
+    const int r_end = min(rows, r_begin + rows_per_cta);
+    int buf = 0;
+    for (int r0 = r_begin; r0 < r_end; r0 += FB_R, buf ^= 1) {
+        float4 xh0[FB_R], xh1[FB_R], a0[FB_R], a1[FB_R];
+        float rs[FB_R];
+        float part[2 * FB_R];
+#pragma unroll
+        for (int j = 0; j < FB_R; ++j) {
+            const int row = r0 + j;
+            const bool ok = row < r_end;
+            const float mean = ok ? mean_in[row] : 0.f;
+            rs[j] = ok ? rstd_in[row] : 0.f;
+            const size_t off = (size_t)(ok ? row : r_begin) * cols;
+            const float4 v0 = ld4(x + off + c0), v1 = ld4(x + off + c1);
+            float4 d0 = ld4(dy + off + c0), d1 = ld4(dy + off + c1);
+            if (!ok) { d0 = make_float4(0.f, 0.f, 0.f, 0.f); d1 = d0; }
+            xh0[j] = make_float4((v0.x - mean) * rs[j], (v0.y - mean) * rs[j], (v0.z - mean) * rs[j], (v0.w - mean) * rs[j]);
+            xh1[j] = make_float4((v1.x - mean) * rs[j], (v1.y - mean) * rs[j], (v1.z - mean) * rs[j], (v1.w - mean) * rs[j]);
+            a0[j] = make_float4(g0.x * d0.x, g0.y * d0.y, g0.z * d0.z, g0.w * d0.w);
+            a1[j] = make_float4(g1.x * d1.x, g1.y * d1.y, g1.z * d1.z, g1.w * d1.w);
+            dg0.x += d0.x * xh0[j].x; dg0.y += d0.y * xh0[j].y; dg0.z += d0.z * xh0[j].z; dg0.w += d0.w * xh0[j].w;
+            dg1.x += d1.x * xh1[j].x; dg1.y += d1.y * xh1[j].y; dg1.z += d1.z * xh1[j].z; dg1.w += d1.w * xh1[j].w;
+            db0.x += d0.x; db0.y += d0.y; db0.z += d0.z; db0.w += d0.w;
+            db1.x += d1.x; db1.y += d1.y; db1.z += d1.z; db1.w += d1.w;
+            part[j] = (a0[j].x + a0[j].y) + (a0[j].z + a0[j].w) + (a1[j].x + a1[j].y) + (a1[j].z + a1[j].w);
+            part[FB_R + j] = (a0[j].x * xh0[j].x + a0[j].y * xh0[j].y) + (a0[j].z * xh0[j].z + a0[j].w * xh0[j].w) +
+                             (a1[j].x * xh1[j].x + a1[j].y * xh1[j].y) + (a1[j].z * xh1[j].z + a1[j].w * xh1[j].w);
+        }
+#pragma unroll
+        for (int t = 0; t < 2 * FB_R; ++t) part[t] = warp_sum(part[t]);
+        if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < 2 * FB_R; ++t) red[buf][warp][t] = part[t];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 2 * FB_R; ++t) {
+            float acc = 0.f;
+            for (int w = 0; w < nwarps; ++w) acc += red[buf][w][t];
+            part[t] = acc * inv_n;
+        }
+#pragma unroll
+        for (int j = 0; j < FB_R; ++j) {
+            const int row = r0 + j;
+            if (row < r_end) {
+                const float s1 = part[j], s2 = part[FB_R + j];
+                const size_t off = (size_t)row * cols;
+                float4 o0, o1;
+                o0.x = rs[j] * (a0[j].x - s1 - xh0[j].x * s2); o0.y = rs[j] * (a0[j].y - s1 - xh0[j].y * s2);
+                o0.z = rs[j] * (a0[j].z - s1 - xh0[j].z * s2); o0.w = rs[j] * (a0[j].w - s1 - xh0[j].w * s2);
+                o1.x = rs[j] * (a1[j].x - s1 - xh1[j].x * s2); o1.y = rs[j] * (a1[j].y - s1 - xh1[j].y * s2);
+                o1.z = rs[j] * (a1[j].z - s1 - xh1[j].z * s2); o1.w = rs[j] * (a1[j].w - s1 - xh1[j].w * s2);
+                if (dres != nullptr) {
+                    const float4 q0 = ld4(dres + off + c0), q1 = ld4(dres + off + c1);
+                    o0.x += q0.x; o0.y += q0.y; o0.z += q0.z; o0.w += q0.w;
+                    o1.x += q1.x; o1.y += q1.y; o1.z += q1.z; o1.w += q1.w;
+                }
+                st4(dx + off + c0, o0);
+                st4(dx + off + c1, o1);
+            }
+        }
+    }
+    float* pout = partials + (size_t)blockIdx.x * 2 * cols;
+    st4(pout + c0, dg0); st4(pout + c1, dg1);
+    st4(pout + cols + c0, db0); st4(pout + cols + c1, db1);
+}
+
 // dgamma[c] = sum_r dy[r,c] * xhat[r,c], dbeta[c] = sum_r dy[r,c].  Thread per column (coalesced across columns),
 // rows split over blockIdx.y; partial sums go to `partials` [gridDim.y, 2, cols], reduced by ln_bwd_finalize.
 constexpr int PARAM_ROW_SPLITS = 32;
@@ -224,7 +309,8 @@ extern "C" int cv_layernorm_absmax_fwd(const void* x, int x_is_bf16, const float
 
 extern "C" int64_t cv_layernorm_bwd_workspace_bytes(int rows, int cols) {
     (void)rows;
-    return (int64_t)PARAM_ROW_SPLITS * 2 * cols * sizeof(float);
+    const int64_t parts = 2 * cvh::num_sms() > PARAM_ROW_SPLITS ? 2 * cvh::num_sms() : PARAM_ROW_SPLITS;
+    return parts * 2 * cols * sizeof(float);
 }
 
 extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16,
@@ -238,6 +324,31 @@ extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void*
     CV_REQUIRE(smem <= 220 * 1024, "hidden size too large for the row cache");
     const int grid = fwd_grid(rows);
     const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gamma);
+    // fused path (parameter gradients in registers, every operand read once)
+    if (cols % 256 == 0 && cols / 8 <= 512) {
+        const int threads = cols / 8;
+        int fgrid = cvh::num_sms();          // 128 registers x cols/8 threads: one CTA per SM
+        int rows_per_cta = (rows + fgrid - 1) / fgrid;
+        rows_per_cta = (rows_per_cta + FB_R - 1) / FB_R * FB_R;
+        fgrid = (rows + rows_per_cta - 1) / rows_per_cta;
+#define LAUNCH_F(TI, TDY, TDX)                                                                                 \
+    ln_bwd_fused_kernel<TI, TDY, TDX><<<fgrid, threads, 0, s>>>(static_cast<const TI*>(x), static_cast<const TDY*>(dy), \
+                                                                mean, rstd, g, dres, static_cast<TDX*>(dx), workspace,   \
+                                                                rows, cols, rows_per_cta)
+        if (x_is_bf16 && !dy_is_bf16 && dx_is_bf16) LAUNCH_F(__nv_bfloat16, float, __nv_bfloat16);
+        else if (!x_is_bf16 && dy_is_bf16 && !dx_is_bf16) LAUNCH_F(float, __nv_bfloat16, float);
+        else if (!x_is_bf16 && !dy_is_bf16 && !dx_is_bf16) LAUNCH_F(float, float, float);
+        else if (x_is_bf16 && dy_is_bf16 && dx_is_bf16) LAUNCH_F(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
+        else return cvh::fail_arg(__func__, "unsupported dtype combination");
+#undef LAUNCH_F
+        CV_LAUNCH_CHECK();
+        const int n2 = 2 * cols;
+        ln_bwd_finalize_kernel<<<(n2 + 255) / 256, 256, 0, s>>>(workspace, fgrid, cols,
+                                                               static_cast<__nv_bfloat16*>(dgamma),
+                                                               static_cast<__nv_bfloat16*>(dbeta));
+        CV_LAUNCH_CHECK();
+        return 0;
+    }
     const int splits = rows < PARAM_ROW_SPLITS ? rows : PARAM_ROW_SPLITS;
     dim3 pgrid((cols + 127) / 128, splits);
 #define LAUNCH(TI, TDY, TDX)                                                                                   \

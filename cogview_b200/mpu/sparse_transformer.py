@@ -187,10 +187,9 @@ def layer_backward(d_out, saved, P, heads, b, sq, sep):
     M = b * sq
     # out = y + LN4(mlp_out)
     d_mlp_out, dg4, db4 = ops.layernorm_absmax_bwd(mlp_out, d_out, mean4, rstd4, g4, dx_dtype=torch.bfloat16)
-    d_h4 = ops.gemm(d_mlp_out, w2, b_mn_major=True)
+    d_pre = ops.gemm(d_mlp_out, w2, b_mn_major=True, act=ops.ACT_GELU_GRAD, aux=pre)   # (dY W2) * gelu'(pre)
     dw2 = ops.gemm(d_mlp_out, h4, a_mn_major=True, b_mn_major=True)
     dbb2 = ops.colsum(d_mlp_out)
-    d_pre = ops.gelu_bwd(pre, d_h4)
     d_ln2 = ops.gemm(d_pre, w1, b_mn_major=True)
     dw1 = ops.gemm(d_pre, ln2, a_mn_major=True, b_mn_major=True)
     dbb1 = ops.colsum(d_pre)

@@ -11,10 +11,11 @@ from ._lib import check, lib, ptr, require_cuda, stream_ptr
 ACT_NONE = 0
 ACT_GELU = 1
 ACT_RELU = 2
+ACT_GELU_GRAD = 3   # multiply the result by gelu'(aux) (GELU backward fused into the dgrad GEMM)
 
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, bias=None, act=ACT_NONE, out_dtype=torch.bfloat16,
-         absmax=None, want_preact=False, out=None, block_n=0):
+         absmax=None, want_preact=False, out=None, block_n=0, aux=None):
     """C[M,N] = op(A)[M,K] @ op(B)[N,K]^T (+bias) (+GELU).
 
     a: [M,K] (or [K,M] when a_mn_major); b: [N,K] (or [K,N] when b_mn_major); both bf16, last dim contiguous.
@@ -37,6 +38,10 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, bias=None, act=ACT_NONE, o
         out = torch.empty((M, N), dtype=out_dtype, device=a.device)
     assert out.stride(1) == 1
     pre = torch.empty((M, N), dtype=torch.bfloat16, device=a.device) if want_preact else None
+    if act == ACT_GELU_GRAD:
+        assert aux is not None and aux.shape == (M, N) and aux.dtype == torch.bfloat16 and not want_preact
+        assert aux.stride(1) == 1 and aux.stride(0) == out.stride(0)
+        pre = aux
     if bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.numel() == N
     rc = lib().cv_gemm_bf16(ptr(a), int(a_mn_major), a.stride(0), ptr(b), int(b_mn_major), b.stride(0),

@@ -37,7 +37,8 @@ long long cv_launch_count(void);
  *   a_mn_major = 0: A stored [M,K] (lda >= K);  1: A stored [K,M] (lda >= M)   (wgrad operand)
  *   b_mn_major = 0: B stored [N,K] (ldb >= K);  1: B stored [K,N] (ldb >= N)   (dgrad/wgrad operand)
  *   C: bf16 (c_is_f32 = 0) or fp32 (c_is_f32 = 1); C2 (optional, bf16, same ld): value before GELU
- *   bias: bf16 [N] or NULL;  act: 0 none, 1 tanh-GELU
+ *   bias: bf16 [N] or NULL;  act: 0 none, 1 tanh-GELU, 2 ReLU, 3 multiply by gelu'(C2) (C2 = saved pre-activation,
+ *         read-only: the GELU backward fused into the dgrad GEMM)
  *   absmax: NULL or device float (must hold a non-negative value): atomic max of |C| — feeds the
  *           reference's abs-max pre-scaled LayerNorm (mpu/sparse_transformer.py:40-44)
  *   block_n: 0 = auto, or 128 / 256
