@@ -38,6 +38,7 @@ def _declare(lib):
         "cv_attn_bwd": [P, L, L, P, L, L, P, L, L, P, P, P, P, P, I, I, I, I, I, P],
         "cv_linear_small_m": [P, L, P, L, P, P, L, I, I, P, I, I, I, P],
         "cv_ln_pair_small_m": [P, P, P, P, P, P, P, F, P, P, I, I, P],
+        "cv_attn_gather": [P, L, L, P, L, P, P, I, I, I, I, I, P],
         "cv_attn_decode": [P, P, L, P, I, P, P, I, I, I, I, I, P],
         "cv_adamw_step": [P, P, P, P, P, L, F, F, F, F, F, I, P, F, P],
         "cv_sumsq_bf16": [P, L, P, P],

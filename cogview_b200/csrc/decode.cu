@@ -417,6 +417,88 @@ __global__ void attn_decode_combine_kernel(const float* __restrict__ partial, __
     out[(size_t)batch * heads * HD + head * HD + d] = __float2bfloat16_rn(A / L);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Attention over a gathered key set (sparse_attention_inference, /root/reference/mpu/sparse_transformer.py:727-750):
+// softmax((q / sqrt(hn)) K[idx]^T + causal(-10000 above the diagonal of the last sq x sq block)) V[idx].
+// One CTA per (head, batch, query); keys come from the K|V cache through the index list (pivots U window).
+// ------------------------------------------------------------------------------------------------
+struct GatherParams {
+    const __nv_bfloat16* q;     // [b, sq, h] view
+    int64_t ldq, bsq;
+    const __nv_bfloat16* cache; // [b, max_len, 2h]
+    int64_t cache_bs;
+    const int64_t* idx;         // [b, n]
+    __nv_bfloat16* out;         // [b, sq, h] contiguous
+    int heads, sq, n;
+    float scale_log2;
+};
+
+__global__ void __launch_bounds__(DA_WARPS * 32)
+attn_gather_kernel(const GatherParams p) {
+    __shared__ float s_m[DA_WARPS * 4], s_l[DA_WARPS * 4];
+    __shared__ float s_acc[DA_WARPS * 4][HD];
+    const int head = blockIdx.x, batch = blockIdx.y, qi = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, sub = lane & 7;
+    const int h = p.heads * HD;
+    float q[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(p.q + (size_t)batch * p.bsq + (size_t)qi * p.ldq + head * HD + sub * 8), q);
+    const __nv_bfloat16* kbase = p.cache + (size_t)batch * p.cache_bs + head * HD + sub * 8;
+    const int64_t* idx = p.idx + (size_t)batch * p.n;
+    const float masked = -10000.0f * 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int jb = warp * 4; jb < p.n; jb += DA_WARPS * 4) {
+        const int j = jb + grp;
+        const bool valid = j < p.n;
+        float kf[8], vf[8];
+        if (valid) {
+            const __nv_bfloat16* kp = kbase + (size_t)idx[j] * 2 * h;
+            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(kp)), kf);
+            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(kp + h)), vf);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(q[i], kf[i], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (valid) {
+            s *= p.scale_log2;
+            const int rel = j - (p.n - p.sq);          // position inside the trailing query block
+            if (p.sq > 1 && rel > qi) s += masked;    // scores + (-10000) above the diagonal (:741-745)
+            const float mn = fmaxf(m, s);
+            const float alpha = exp2f(m - mn), pr = exp2f(s - mn);
+            m = mn;
+            l = l * alpha + pr;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = acc[i] * alpha + pr * vf[i];
+        }
+    }
+    const int slot = warp * 4 + grp;
+    if (sub == 0) { s_m[slot] = m; s_l[slot] = l; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_acc[slot][sub * 8 + i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < HD) {
+        const int d = threadIdx.x;
+        float M = -INFINITY;
+        for (int sidx = 0; sidx < DA_WARPS * 4; ++sidx) M = fmaxf(M, s_m[sidx]);
+        float L = 0.f, A = 0.f;
+        for (int sidx = 0; sidx < DA_WARPS * 4; ++sidx) {
+            const float w = (s_m[sidx] == -INFINITY) ? 0.f : exp2f(s_m[sidx] - M);
+            L += s_l[sidx] * w;
+            A += s_acc[sidx][d] * w;
+        }
+        p.out[((size_t)batch * p.sq + qi) * h + head * HD + d] = __float2bfloat16_rn(A / L);
+    }
+}
+
 }  // namespace
 
 extern "C" int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out,
@@ -514,5 +596,23 @@ extern "C" int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_
                                 static_cast<const float*>(workspace), static_cast<__nv_bfloat16*>(out), heads, nsplit));
         cvh::count_launches(1);
     }
+    return 0;
+}
+
+extern "C" int cv_attn_gather(const void* q, int64_t ldq, int64_t bsq, const void* cache, int64_t cache_batch_stride,
+                              const int64_t* idx, void* out, int b, int heads, int head_dim, int sq, int n,
+                              void* stream) {
+    CV_REQUIRE(q && cache && idx && out, "null pointer");
+    CV_REQUIRE(head_dim == HD, "head_dim must be 64");
+    CV_REQUIRE(b > 0 && heads > 0 && sq > 0 && n >= sq, "need n >= sq > 0 (the last sq indices are the queries)");
+    CV_REQUIRE(sq <= 65535 && b <= 65535, "grid dimension limit");
+    GatherParams p;
+    p.q = static_cast<const __nv_bfloat16*>(q); p.ldq = ldq; p.bsq = bsq;
+    p.cache = static_cast<const __nv_bfloat16*>(cache); p.cache_bs = cache_batch_stride;
+    p.idx = idx; p.out = static_cast<__nv_bfloat16*>(out);
+    p.heads = heads; p.sq = sq; p.n = n;
+    p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
+    attn_gather_kernel<<<dim3(heads, b, sq), DA_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    CV_LAUNCH_CHECK();
     return 0;
 }

@@ -80,17 +80,17 @@ class GPT2Model(torch.nn.Module):
         """Same positional arguments as the reference (model/gpt2_modeling.py:106).  Returns
         (logits [b, s, V] fp32, *mems).  `logits_last_only` (keyword, extension): only the last position's
         logits are computed — what the sampling loop reads (generation/sampling.py:155)."""
-        if is_sparse != 0:
-            raise NotImplementedError('sparse attention (is_sparse=%d) is not implemented in this round' % is_sparse)
+        if is_sparse == 1:
+            raise NotImplementedError('sparse training (is_sparse=1) is not implemented in this round')
         tr = self.transformer
         if tr.training and tr.embedding_dropout_prob > 0:
             raise NotImplementedError('embedding dropout > 0 is not supported yet')
         b, sq = input_ids.shape
         mem_len = mems[0].size(1) if mems else 0
-        sep = mask_to_sep(attention_mask, sq, sq + mem_len)
+        sep = 0 if is_sparse == 2 else mask_to_sep(attention_mask, sq, sq + mem_len)
         if position_ids.shape != input_ids.shape:
             position_ids = position_ids.expand_as(input_ids)
-        fast = self._fast_decode(input_ids, position_ids, mems, b, sq)
+        fast = self._fast_decode(input_ids, position_ids, mems, b, sq) if is_sparse == 0 else None
         if fast is not None:
             return fast
         wte, wpe = self.word_embeddings.weight, tr.position_embeddings.weight
@@ -100,7 +100,8 @@ class GPT2Model(torch.nn.Module):
             am_x = ops.new_scalars(1, wte.device)
             x = ops.embed_fwd(input_ids, position_ids, _as_bf16(wte.detach()).contiguous(),
                               _as_bf16(wpe.detach()).contiguous(), am_x)
-        y, mem_layers = tr.run_layers(x, am_x, b, sq, sep, mems)
+        y, mem_layers = tr.run_layers(x, am_x, b, sq, sep, mems, is_sparse=is_sparse,
+                                      txt_indices_bool=txt_indices_bool, img_indices_bool=img_indices_bool)
         h = y.shape[1]
         if logits_last_only:
             y = y.view(b, sq, h)[:, -1].contiguous()

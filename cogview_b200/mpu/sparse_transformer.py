@@ -139,7 +139,7 @@ _PARAM_ORDER = ('input_layernorm.weight', 'input_layernorm.bias',
                 'fourth_layernorm.weight', 'fourth_layernorm.bias')
 
 
-def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None):
+def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None, attn=None):
     """One Sandwich-LN block (mpu/sparse_transformer.py:314-342) on the fp32 residual stream x [b*sq, h].
 
     am_x: 1-element fp32 tensor holding max|x|.  P: the 16 parameters in _PARAM_ORDER (bf16).
@@ -156,7 +156,9 @@ def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None):
     q, k, v = qkv3[..., :h], qkv3[..., h:2 * h], qkv3[..., 2 * h:]
     if kv is not None:
         k, v = kv(k, v)
-    if training:
+    if attn is not None:            # sparse inference: attention over a gathered key set
+        ctx, lse = attn(q), None
+    elif training:
         ctx, lse = ops.attn_fwd(q, k, v, heads, sep=sep, want_lse=True)
     else:
         ctx, lse = ops.attn_fwd(q, k, v, heads, sep=sep), None
@@ -354,7 +356,7 @@ class GPT2ParallelTransformerLayer(torch.nn.Module):
             raise NotImplementedError('dropout > 0 in training mode is not supported by the fused layer yet; '
                                       'construct the model with dropout probabilities 0 (parity runs do)')
 
-    def fused_forward(self, x, am_x, b, sq, sep, kv=None):
+    def fused_forward(self, x, am_x, b, sq, sep, kv=None, attn=None):
         """x: fp32 [b*sq, h] residual stream, am_x: max|x| scalar tensor -> (out, am_out)."""
         self._check_dropout()
         params = self.param_list()
@@ -363,7 +365,7 @@ class GPT2ParallelTransformerLayer(torch.nn.Module):
                 raise NotImplementedError('training with memory is not supported')
             return _LayerFn.apply(x, am_x, self.num_attention_heads, self.layernorm_epsilon, b, sq, sep, *params)
         P = tuple(_as_bf16(p.detach()) for p in params)
-        return layer_forward(x, am_x, P, self.num_attention_heads, self.layernorm_epsilon, b, sq, sep, kv=kv)
+        return layer_forward(x, am_x, P, self.num_attention_heads, self.layernorm_epsilon, b, sq, sep, kv=kv, attn=attn)
 
     def forward(self, hidden_states, ltor_mask, pivot_idx=None, is_sparse=0, mem=None):
         """Reference signature: hidden_states [b, s, h], mask [1,1,s,s] or int sep; `mem` = hidden-state memory
@@ -469,7 +471,30 @@ class GPT2ParallelTransformer(torch.nn.Module):
         self._kv = None
 
     # -- the stack on the fp32 residual stream ---------------------------------------------------------
-    def run_layers(self, x, am_x, b, sq, sep, mems, word_embedding_weight=None):
+    def sparse_index_plan(self, key_length, txt_indices_bool, img_indices_bool, b, device):
+        """Index bookkeeping of is_sparse == 2 (mpu/sparse_transformer.py:498-520): trailing window, text / image
+        positions before it, and the pivot count."""
+        w, times = self.query_window, self.key_window_times
+        left_boundary = max(0, key_length - times * w)
+        window_idx = torch.arange(left_boundary, key_length, device=device, dtype=torch.long).expand(b, -1)
+        img_indices = [img_indices_bool[i][:left_boundary].nonzero(as_tuple=False).view(-1) for i in range(b)]
+        txt_indices = [txt_indices_bool[i][:left_boundary].nonzero(as_tuple=False).view(-1) for i in range(b)]
+        ratio = self.num_pivot / self.max_sequence_length
+        max_text_num = max(len(t) for t in txt_indices)
+        num_pivot = max_text_num + int((left_boundary - max_text_num) * ratio)
+        return window_idx, img_indices, txt_indices, num_pivot
+
+    def sample_pivots(self, window_idx, img_indices, txt_indices, num_pivot):
+        """Fresh pivots for one layer (:591-600): all text positions + a Python random.sample of image positions."""
+        pivot_idx = torch.stack([
+            torch.cat((text_idx,
+                       img_indices[i][torch.tensor(random.sample(range(len(img_indices[i])), k=num_pivot - len(text_idx)),
+                                                   dtype=torch.long, device=text_idx.device)]), dim=0)
+            for i, text_idx in enumerate(txt_indices)])
+        return torch.cat((pivot_idx, window_idx), dim=-1)
+
+    def run_layers(self, x, am_x, b, sq, sep, mems, word_embedding_weight=None, is_sparse=0, txt_indices_bool=None,
+                   img_indices_bool=None):
         """x fp32 [b*sq, h].  Returns (final-LN output bf16 [b*sq, h], mem_layers list)."""
         from . import kv_cache
         h = self.hidden_size
@@ -481,8 +506,25 @@ class GPT2ParallelTransformer(torch.nn.Module):
             mode = 'hidden'   # training forward: return the reference's detached hidden-state mems
         hidden_mems = [x.detach().view(b, sq, h)] if mode == 'hidden' else []
         caches = kv_cache.prepare(self, mems, b, sq) if mode == 'kv' else None
+        plan = None
+        if is_sparse == 2:
+            if mode != 'kv' or torch.is_grad_enabled():
+                raise NotImplementedError("is_sparse=2 (sparse inference) needs max_memory_length > 0, mems_mode 'kv' "
+                                          "and torch.no_grad()")
+            if sq > self.query_window * self.key_window_times:
+                raise ValueError('the fed tokens must fit in the attention window (query_window * key_window_times)')
+            plan = self.sparse_index_plan(caches.t + sq, txt_indices_bool, img_indices_bool, b, x.device)
+        elif is_sparse != 0:
+            raise NotImplementedError('sparse training (is_sparse=1) is not implemented in this round')
         for i, layer in enumerate(self.layers):
-            if mode == 'kv':
+            if mode == 'kv' and plan is not None:
+                pw_idx = self.sample_pivots(*plan)
+                cache_i, t_all, heads = caches.buf[i], caches.t + sq, self.num_attention_heads
+
+                def gather_attn(q, cache_i=cache_i, pw_idx=pw_idx):
+                    return ops.attn_gather(q, cache_i[:, :t_all], pw_idx, heads)
+                out, am_x = layer.fused_forward(x, am_x, b, sq, sep, kv=caches.appender(i), attn=gather_attn)
+            elif mode == 'kv':
                 out, am_x = layer.fused_forward(x, am_x, b, sq, sep, kv=caches.appender(i))
             elif mems:   # hidden-state memory: exact reference semantics
                 out = layer(x.view(b, sq, h), sep, mem=mems[i]).view(b * sq, h)
@@ -514,17 +556,18 @@ class GPT2ParallelTransformer(torch.nn.Module):
                 *mems):
         """Reference signature (mpu/sparse_transformer.py:471): hidden_states = word embeddings [b, s, h].
         Returns (final-LN output [b, s, h], *mems)."""
-        if is_sparse != 0:
-            raise NotImplementedError('sparse attention (is_sparse=%d) is not implemented in this round' % is_sparse)
+        if is_sparse == 1:
+            raise NotImplementedError('sparse training (is_sparse=1) is not implemented in this round')
         b, sq, h = hidden_states.shape
         mem_len = mems[0].size(1) if mems else 0
-        sep = mask_to_sep(attention_mask, sq, sq + mem_len)
+        sep = 0 if is_sparse == 2 else mask_to_sep(attention_mask, sq, sq + mem_len)
         if self.training and self.embedding_dropout_prob > 0:
             raise NotImplementedError('embedding dropout > 0 is not supported yet')
         pe = torch.nn.functional.embedding(position_ids, self.position_embeddings.weight)
         x = (hidden_states.float() + pe.float()).reshape(b * sq, h).contiguous()
         am_x = ops.absmax(x.detach())
-        y, mem_layers = self.run_layers(x, am_x, b, sq, sep, mems)
+        y, mem_layers = self.run_layers(x, am_x, b, sq, sep, mems, is_sparse=is_sparse,
+                                        txt_indices_bool=txt_indices_bool, img_indices_bool=img_indices_bool)
         return (y.view(b, sq, h).to(hidden_states.dtype), *mem_layers)
 
     def update_mems(self, hiddens, mems):
@@ -566,6 +609,13 @@ def sparse_attention(*args, **kwargs):
     raise NotImplementedError('sparse_attention is not implemented in this round')
 
 
-def sparse_attention_inference(*args, **kwargs):
-    """mpu/sparse_transformer.py:727-750 — not implemented in this round."""
-    raise NotImplementedError('sparse_attention_inference is not implemented in this round')
+def sparse_attention_inference(q, k, v, pivot_and_window_idx, **kwargs):
+    """mpu/sparse_transformer.py:727-750 on [b, np, s, hn] tensors (API parity; the model path reads the K|V cache in
+    place): dense softmax over K[idx], V[idx] with the causal fix for the trailing queries."""
+    b, nh, sq, hn = q.shape
+    sk = k.shape[2]
+    kv = torch.cat((_as_bf16(k).permute(0, 2, 1, 3).reshape(b, sk, nh * hn),
+                    _as_bf16(v).permute(0, 2, 1, 3).reshape(b, sk, nh * hn)), dim=-1).contiguous()
+    qt = _as_bf16(q).permute(0, 2, 1, 3).reshape(b, sq, nh * hn).contiguous()
+    ctx = ops.attn_gather(qt, kv, pivot_and_window_idx, nh)
+    return ctx.view(b, sq, nh, hn).permute(0, 2, 1, 3).to(q.dtype)

@@ -342,3 +342,16 @@ def conv1x1_out3(x, w, bias, scale, shift):
     check(lib().cv_conv1x1_out3(ptr(x), ptr(w), ptr(bias), ptr(scale), ptr(shift), ptr(out), B, H, W, Cin,
                                 stream_ptr()), "cv_conv1x1_out3")
     return out
+
+
+def attn_gather(q, cache, idx, heads):
+    """sparse_attention_inference: q [b, sq, h] view, cache [b, max_len, 2h] (K|V), idx [b, n] int64 -> [b, sq, h]."""
+    require_cuda(q, cache, idx)
+    b, sq, h = q.shape
+    assert q.stride(2) == 1 and cache.stride(2) == 1 and cache.stride(1) == 2 * h and idx.dtype == torch.int64
+    idx = idx.contiguous()
+    out = torch.empty((b, sq, h), dtype=torch.bfloat16, device=q.device)
+    rc = lib().cv_attn_gather(ptr(q), q.stride(1), q.stride(0), ptr(cache), cache.stride(0), ptr(idx), ptr(out), b, heads,
+                              64, sq, idx.shape[1], stream_ptr())
+    check(rc, "cv_attn_gather")
+    return out

@@ -133,6 +133,12 @@ int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int64_t ldw, co
 int cv_ln_pair_small_m(const float* res_in, const void* gemm_out, const float* absmax_gemm, const void* g_post,
                        const void* b_post, const void* g_pre, const void* b_pre, float eps, float* res_out,
                        void* xn_out, int M, int K, void* stream);
+/* sparse_attention_inference (mpu/sparse_transformer.py:727-750): dense softmax over the gathered keys
+ * K[idx], V[idx] (idx = pivots U trailing window, [b, n] int64; its last sq entries are the queries' own positions,
+ * which get the causal -10000 above the diagonal).  q: [b, sq, heads*64] view; cache [b, max_len, 2*heads*64] (K|V)
+ * already holding the new tokens; out [b, sq, heads*64] bf16 contiguous. */
+int cv_attn_gather(const void* q, int64_t ldq, int64_t bsq, const void* cache, int64_t cache_batch_stride,
+                   const int64_t* idx, void* out, int b, int heads, int head_dim, int sq, int n, void* stream);
 int64_t cv_attn_decode_workspace_bytes(int b, int heads, int nsplit);
 int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_stride, const int* cur_len_dev, int cur_len,
                    void* out, float* workspace, int b, int heads, int head_dim, int max_len, int nsplit,

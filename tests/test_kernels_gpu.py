@@ -235,3 +235,21 @@ def test_ln_pair_small_m(ops, M, K):
     assert rel_err(y, y_ref) < 1e-5 and rel_err(xn, xn_ref) < 1e-2
     _, xn0 = ops.ln_pair_small_m(res.cuda(), None, None, None, (gq.cuda(), bq.cuda()), 1e-5, want_res_out=False)
     assert rel_err(xn0, O.layernorm_absmax(res, gq.float(), bq.float())) < 1e-2
+
+
+def test_attn_gather_matches_sparse_attention_inference(ops, golden_dir):
+    """cv_attn_gather vs the oracle's sparse_attention_inference and the reference's golden output."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "attention.npz"))
+    b, nh, s, hn, w, times, n_piv, sq = [int(x) for x in g["dims"]]
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    q, k, v = (torch.randn((b, nh, s, hn), generator=gen) for _ in range(3))
+    pivot_idx = torch.from_numpy(g["pivot_idx"])
+    pw = torch.cat((pivot_idx, torch.arange(s - times * w, s).expand(b, -1)), dim=-1)
+    qb, kb, vb = bf(q), bf(k), bf(v)
+    ref = O.sparse_attention_inference(qb.float()[:, :, -sq:], kb.float(), vb.float(), pw)
+    from cogview_b200.mpu.sparse_transformer import sparse_attention_inference
+    out = sparse_attention_inference(qb[:, :, -sq:].cuda(), kb.cuda(), vb.cuda(), pw.cuda())
+    assert rel_err(out, ref) < 1e-2
+    assert np.abs(out.float().cpu().numpy() - g["sparse_infer"]).max() < 2e-2 * np.abs(g["sparse_infer"]).max()

@@ -168,3 +168,26 @@ def test_training_step_loss_and_grads(data, ckpt):
         rn = float(g["grad_norms"][names.index(n)])
         assert abs(gn - rn) < 5e-2 * rn, (n, gn, rn)
     print("worst relative gradient error: %s %.3e" % worst)
+
+
+def test_sparse_inference_equals_dense_when_window_covers_everything(data):
+    """is_sparse=2 (mpu/sparse_transformer.py:498-520, 727-750): with key_length <= query_window * key_window_times the
+    gathered key set is every key, so sparse decode must reproduce the dense KV-cache decode."""
+    m = build(max_memory_length=CFG["max_sequence_length"], mems_mode="kv").eval()
+    ctx = data["tokens"][:, :64].cuda()
+    pos = data["pos"][:, :64].cuda()
+    with torch.no_grad():
+        img = ctx < recipes.IMG_VOCAB
+        lg_s, *mems_s = m(ctx, pos, torch.tril(torch.ones((1, 1, 64, 64), device="cuda")), ~img, img, 2)
+        lg_d, *mems_d = build(max_memory_length=CFG["max_sequence_length"], mems_mode="kv").eval()(
+            ctx, pos, torch.tril(torch.ones((1, 1, 64, 64), device="cuda")), None, None, 0)
+        scale = lg_d.abs().max().item()
+        assert (lg_s - lg_d).abs().max().item() < 2e-2 * scale
+        toks = ctx
+        for t in range(64, 68):
+            nxt = lg_s[:, -1, :recipes.IMG_VOCAB].float().argmax(-1, keepdim=True)
+            toks = torch.cat((toks, nxt), dim=1)
+            img = toks < recipes.IMG_VOCAB
+            p = torch.full((2, 1), t, dtype=torch.long, device="cuda")
+            lg_s, *mems_s = m(nxt, p, 0, ~img, img, 2, *mems_s)
+        assert mems_s[0].size(1) == 68 and bool(torch.isfinite(lg_s).all())
