@@ -18,8 +18,8 @@ using namespace cv;
 // ------------------------------------------------------------------------------------------------
 // skinny linear on warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 x bf16 -> fp32).
 //
-// A CTA owns 16 output columns (16 rows of W); its 8 warps split K, so a 2560-column layer still puts
-// 160 x 8 warps on the machine.  Per 32-element K chunk a lane issues two 16-byte loads of W (rows g and g+8,
+// 2 x 148 CTAs each own a contiguous, byte-balanced range of output columns (rows of W) walked in MMA tiles of 16;
+// the CTA's 8 warps split K, so even a 2560-column layer keeps 296 x 8 warps streaming.  Per 32-element K chunk a lane issues two 16-byte loads of W (rows g and g+8,
 // elements 8q..8q+7; g = lane/4, q = lane%4) and one 16-byte load of x (row g): because a dot product does not
 // care in which order k is summed, those 8 contiguous elements are fed to two MMAs as the fragment slots
 // {2q,2q+1,2q+8,2q+9}, with x permuted identically — so both operands are read with full 16-byte, sector-exact
@@ -29,7 +29,7 @@ using namespace cv;
 // ------------------------------------------------------------------------------------------------
 constexpr int SK_WARPS = 8;
 constexpr int SK_NT = 16;         // output columns per CTA
-constexpr int SK_UNROLL = 4;      // K chunks (of 32) per register stage
+constexpr int SK_UNROLL = 8;      // K chunks (of 32) in flight per warp: 512 contiguous bytes of each of its 16 rows
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -63,93 +63,103 @@ struct SkStage {
     uint4 w0[SK_UNROLL], w1[SK_UNROLL], xv[SK_UNROLL];
 };
 
-__global__ void __launch_bounds__(SK_WARPS * 32)
+__global__ void __launch_bounds__(SK_WARPS * 32, 2)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ W,
                       int64_t ldw, const __nv_bfloat16* __restrict__ bias, void* __restrict__ out, int64_t ldo,
                       int out_f32, int act, float* __restrict__ absmax, int M, int N, int K) {
-    __shared__ float part[SK_WARPS][SK_NT][8];
+    __shared__ float part[2][SK_WARPS][SK_NT][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int n0 = blockIdx.x * SK_NT;
+    // Byte-balanced split: CTA i owns the contiguous output columns [N*i/G, N*(i+1)/G) — with G = 2 x SM count every
+    // SM streams the same number of weight rows (to within one), whatever N is; the range is walked in MMA tiles
+    // of 16 rows with the rows beyond the range masked off (not loaded).
+    const int c_lo = (int)(((int64_t)N * blockIdx.x) / gridDim.x);
+    const int c_hi = (int)(((int64_t)N * (blockIdx.x + 1)) / gridDim.x);
     const int nchunks = (K + 31) / 32;
     const int per_warp = (nchunks + SK_WARPS - 1) / SK_WARPS;
     const int c_begin = warp * per_warp, c_end = min(nchunks, c_begin + per_warp);
-    const bool r0_ok = n0 + g < N, r1_ok = n0 + g + 8 < N, x_ok = g < M;
-    const __nv_bfloat16* wrow0 = W + (size_t)(n0 + g) * ldw + q * 8;
-    const __nv_bfloat16* wrow1 = W + (size_t)(n0 + g + 8) * ldw + q * 8;
+    const bool x_ok = g < M;
     const __nv_bfloat16* xrow = x + (size_t)g * ldx + q * 8;
     const uint4 zero = make_uint4(0, 0, 0, 0);
-
     const uint64_t pol = make_evict_first_policy();
-    auto load_w = [&](int c0, SkStage& st) {
-#pragma unroll
-        for (int u = 0; u < SK_UNROLL; ++u) {
-            const int c = c0 + u;
-            const bool in = c < c_end && c * 32 + q * 8 < K;
-            st.w0[u] = (in && r0_ok) ? ld_stream(wrow0 + (size_t)c * 32, pol) : zero;
-            st.w1[u] = (in && r1_ok) ? ld_stream(wrow1 + (size_t)c * 32, pol) : zero;
-        }
-    };
-    auto load_x = [&](int c0, SkStage& st) {
-#pragma unroll
-        for (int u = 0; u < SK_UNROLL; ++u) {
-            const int c = c0 + u;
-            const bool in = c < c_end && c * 32 + q * 8 < K;
-            st.xv[u] = (in && x_ok) ? *reinterpret_cast<const uint4*>(xrow + (size_t)c * 32) : zero;
-        }
-    };
-    auto load_stage = [&](int c0, SkStage& st) {
-        load_w(c0, st);
-        load_x(c0, st);
-    };
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-    auto consume = [&](const SkStage& st) {
-#pragma unroll
-        for (int u = 0; u < SK_UNROLL; ++u) {
-            mma_bf16_16816(d, st.w0[u].x, st.w1[u].x, st.w0[u].y, st.w1[u].y, st.xv[u].x, st.xv[u].y);
-            mma_bf16_16816(d, st.w0[u].z, st.w1[u].z, st.w0[u].w, st.w1[u].w, st.xv[u].z, st.xv[u].w);
-        }
-    };
-    SkStage sa, sb;
-    // weights do not depend on the previous kernel: request them, let the next kernel start its own prologue,
-    // and only then wait for the producer of x
-    load_w(c_begin, sa);
-    load_w(c_begin + SK_UNROLL, sb);
-    pdl_launch_dependents();
-    pdl_wait();
-    load_x(c_begin, sa);
-    load_x(c_begin + SK_UNROLL, sb);
-    for (int c = c_begin; c < c_end; c += 2 * SK_UNROLL) {
-        consume(sa);
-        load_stage(c + 2 * SK_UNROLL, sa);
-        consume(sb);
-        load_stage(c + 3 * SK_UNROLL, sb);
-    }
-    // D fragment: d0,d1 = (row g, cols 2q,2q+1), d2,d3 = (row g+8, cols 2q,2q+1); row = output column, col = m
-    part[warp][g][2 * q] = d[0];
-    part[warp][g][2 * q + 1] = d[1];
-    part[warp][g + 8][2 * q] = d[2];
-    part[warp][g + 8][2 * q + 1] = d[3];
-    __syncthreads();
     float tmax = 0.f;
-    if (threadIdx.x < SK_NT * 8) {
-        const int m = threadIdx.x >> 4, nn = threadIdx.x & 15;   // consecutive threads -> consecutive columns
-        float v = 0.f;
+    bool waited = false;
+    int buf = 0;
+    for (int n0 = c_lo; n0 < c_hi; n0 += SK_NT, buf ^= 1) {
+        const bool r0_ok = n0 + g < c_hi, r1_ok = n0 + g + 8 < c_hi;
+        const __nv_bfloat16* wrow0 = W + (size_t)(n0 + g) * ldw + q * 8;
+        const __nv_bfloat16* wrow1 = W + (size_t)(n0 + g + 8) * ldw + q * 8;
+        auto load_w = [&](int c0, SkStage& st) {
 #pragma unroll
-        for (int w = 0; w < SK_WARPS; ++w) v += part[w][nn][m];
-        const int n = n0 + nn;
-        if (m < M && n < N) {
-            if (bias != nullptr) v += __bfloat162float(bias[n]);
-            if (act == 1) v = gelu_tanh(v);
-            if (out_f32) {
-                static_cast<float*>(out)[(size_t)m * ldo + n] = v;
-                tmax = fabsf(v);
-            } else {
-                const __nv_bfloat16 o = __float2bfloat16_rn(v);
-                static_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + n] = o;
-                tmax = fabsf(__bfloat162float(o));
+            for (int u = 0; u < SK_UNROLL; ++u) {
+                const int c = c0 + u;
+                const bool in = c < c_end && c * 32 + q * 8 < K;
+                st.w0[u] = (in && r0_ok) ? ld_stream(wrow0 + (size_t)c * 32, pol) : zero;
+                st.w1[u] = (in && r1_ok) ? ld_stream(wrow1 + (size_t)c * 32, pol) : zero;
+            }
+        };
+        auto load_x = [&](int c0, SkStage& st) {
+#pragma unroll
+            for (int u = 0; u < SK_UNROLL; ++u) {
+                const int c = c0 + u;
+                const bool in = c < c_end && c * 32 + q * 8 < K;
+                st.xv[u] = (in && x_ok) ? *reinterpret_cast<const uint4*>(xrow + (size_t)c * 32) : zero;
+            }
+        };
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        SkStage st;
+        // weights do not depend on the previous kernel: request them, let the next kernel start its own prologue,
+        // and only then wait for the producer of x
+        load_w(c_begin, st);
+        if (!waited) {
+            pdl_launch_dependents();
+            pdl_wait();
+            waited = true;
+        }
+        load_x(c_begin, st);
+        // rolling prefetch: slot u is refilled with chunk c + SK_UNROLL + u right after it has been consumed, so each
+        // warp keeps SK_UNROLL chunks (512 B of each of its 16 weight rows) in flight from one register set
+        for (int c = c_begin; c < c_end; c += SK_UNROLL) {
+#pragma unroll
+            for (int u = 0; u < SK_UNROLL; ++u) {
+                mma_bf16_16816(d, st.w0[u].x, st.w1[u].x, st.w0[u].y, st.w1[u].y, st.xv[u].x, st.xv[u].y);
+                mma_bf16_16816(d, st.w0[u].z, st.w1[u].z, st.w0[u].w, st.w1[u].w, st.xv[u].z, st.xv[u].w);
+                const int cn = c + SK_UNROLL + u;
+                const bool in = cn < c_end && cn * 32 + q * 8 < K;
+                st.w0[u] = (in && r0_ok) ? ld_stream(wrow0 + (size_t)cn * 32, pol) : zero;
+                st.w1[u] = (in && r1_ok) ? ld_stream(wrow1 + (size_t)cn * 32, pol) : zero;
+                st.xv[u] = (in && x_ok) ? *reinterpret_cast<const uint4*>(xrow + (size_t)cn * 32) : zero;
             }
         }
+        // D fragment: d0,d1 = (row g, cols 2q,2q+1), d2,d3 = (row g+8, cols 2q,2q+1); row = output column, col = m
+        part[buf][warp][g][2 * q] = d[0];
+        part[buf][warp][g][2 * q + 1] = d[1];
+        part[buf][warp][g + 8][2 * q] = d[2];
+        part[buf][warp][g + 8][2 * q + 1] = d[3];
+        __syncthreads();
+        if (threadIdx.x < SK_NT * 8) {
+            const int m = threadIdx.x >> 4, nn = threadIdx.x & 15;   // consecutive threads -> consecutive columns
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < SK_WARPS; ++w) v += part[buf][w][nn][m];
+            const int n = n0 + nn;
+            if (m < M && n < c_hi) {
+                if (bias != nullptr) v += __bfloat162float(bias[n]);
+                if (act == 1) v = gelu_tanh(v);
+                if (out_f32) {
+                    static_cast<float*>(out)[(size_t)m * ldo + n] = v;
+                    tmax = fmaxf(tmax, fabsf(v));
+                } else {
+                    const __nv_bfloat16 o = __float2bfloat16_rn(v);
+                    static_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + n] = o;
+                    tmax = fmaxf(tmax, fabsf(__bfloat162float(o)));
+                }
+            }
+        }
+    }
+    if (!waited) {       // empty column range: still take part in the launch chain
+        pdl_launch_dependents();
+        pdl_wait();
     }
     if (absmax != nullptr && warp < 4) {
         tmax = warp_max(tmax);
@@ -511,7 +521,8 @@ extern "C" int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int6
                "x and W must be 16-byte aligned");
     CV_REQUIRE(act == 0 || act == 1, "act must be 0 or 1");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int grid = (N + SK_NT - 1) / SK_NT;
+    int grid = 2 * cvh::num_sms();                       // byte-balanced column ranges, two CTAs per SM
+    if (grid > (N + 7) / 8) grid = (N + 7) / 8;          // tiny N: at least ~8 columns per CTA
     const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
     const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(W);
     const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(bias);
