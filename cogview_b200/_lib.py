@@ -30,12 +30,13 @@ def _declare(lib):
                          c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     }
     P, I, L, F = c_void_p, c_int, c_int64, c_float
+    U64, U32 = ctypes.c_uint64, ctypes.c_uint32
     sigs.update({
         "cv_layernorm_absmax_fwd": [P, I, P, P, P, F, P, P, I, P, P, P, I, I, P],
-        "cv_layernorm_absmax_bwd": [P, I, P, I, P, P, P, P, P, I, P, P, P, I, I, P],
+        "cv_layernorm_absmax_bwd": [P, I, P, I, P, P, P, P, P, I, P, P, P, I, I, F, U64, U32, P],
         "cv_absmax": [P, I, L, P, P],
-        "cv_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, P],
-        "cv_attn_bwd": [P, L, L, P, L, L, P, L, L, P, P, P, P, P, I, I, I, I, I, P],
+        "cv_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, F, U64, U32, P, P],
+        "cv_attn_bwd": [P, L, L, P, L, L, P, L, L, P, P, P, P, P, I, I, I, I, I, F, P, P],
         "cv_linear_small_m": [P, L, P, L, P, P, L, I, I, P, I, I, I, P],
         "cv_ln_pair_small_m": [P, P, P, P, P, P, P, F, P, P, I, I, P],
         "cv_attn_gather": [P, L, L, P, L, P, P, I, I, I, I, I, P],
@@ -50,8 +51,10 @@ def _declare(lib):
         "cv_vq_argmin": [P, L, P, P, P, P, L, I, I, F, P],
         "cv_vq_lookup": [P, P, P, P, L, I, P],
         "cv_conv1x1_out3": [P, P, P, P, P, P, I, I, I, I, P],
-        "cv_embed_fwd": [P, P, P, P, P, P, I, I, P],
-        "cv_embed_bwd": [P, P, P, P, P, I, I, P],
+        "cv_embed_fwd": [P, P, P, P, P, P, I, I, F, U64, U32, P],
+        "cv_embed_bwd": [P, P, P, P, P, I, I, F, U64, U32, P],
+        "cv_dropout_mask": [P, L, F, U64, U32, P],
+        "cv_gemm_bf16_dropout": [P, I, L, P, I, L, P, I, L, P, P, I, P, I, I, I, I, F, U64, U32, P],
         "cv_cross_entropy_fwd": [P, L, P, P, P, P, I, I, P],
         "cv_cross_entropy_bwd": [P, L, P, P, P, P, P, L, I, I, P],
         "cv_gelu_bwd": [P, P, P, L, P],

@@ -29,7 +29,7 @@ constexpr int TILE_BYTES = BLK * HD * 2;      // 16 KB: one [128 x 64] bf16 tile
 constexpr int PT_BYTES = BLK * BLK * 2;       // 32 KB: [128 keys x 128 queries] bf16
 constexpr int QDO_STAGES = 2;
 constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + QDO_STAGES * 2 * TILE_BYTES /*Q,dO*/ + 2 * PT_BYTES /*P^T,dS^T*/ +
-                           QDO_STAGES * 2 * BLK * 4 /*lse2, D*/ + 1024 + 256;
+                           QDO_STAGES * 2 * BLK * 4 /*lse2, D*/ + QDO_STAGES * BLK * 16 /*keep bits*/ + 1024 + 256;
 constexpr int NUM_THREADS = 192;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -41,6 +41,8 @@ struct BwdParams {
     const float* delta;  // [b, heads, s]
     float* dq_acc;       // [b, s, heads*HD] fp32, zero-initialised
     __nv_bfloat16* dqkv; // [b, s, 3*heads*HD]
+    const uint32_t* drop_mask;  // keep bits written by the forward ([b, heads, s, nkb, 4]) or null (no dropout)
+    float drop_scale;           // 1 / (1 - p)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -60,7 +62,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* sDST = sPT + PT_BYTES;
     float* sLse = reinterpret_cast<float*>(sDST + PT_BYTES);       // [stages][128]
     float* sDelta = sLse + QDO_STAGES * BLK;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + QDO_STAGES * BLK);
+    uint4* sKeep = reinterpret_cast<uint4*>(sDelta + QDO_STAGES * BLK);   // [stages][128 queries] 128 keep bits each
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKeep + QDO_STAGES * BLK);
     uint64_t* kv_full = bars;                  // 1
     uint64_t* qdo_full = bars + 1;             // [2]
     uint64_t* qdo_empty = qdo_full + QDO_STAGES;
@@ -182,6 +185,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const int qi = q0 + epi_tid;
                 sLse[stage * BLK + epi_tid] = (qi < p.s) ? p.lse[stat_base + qi] * LOG2E : 0.f;
                 sDelta[stage * BLK + epi_tid] = (qi < p.s) ? p.delta[stat_base + qi] : 0.f;
+                if (p.drop_mask != nullptr)
+                    sKeep[stage * BLK + epi_tid] = (qi < p.s)
+                        ? *reinterpret_cast<const uint4*>(p.drop_mask + ((stat_base + qi) * (size_t)nqb + kb) * 4)
+                        : make_uint4(0, 0, 0, 0);
             }
             named_bar_sync(1, 128);
             mbar_wait(sdp_full, t & 1);
@@ -191,6 +198,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                   ((k0 + BLK <= p.sep_eff) || (k0 + BLK - 1 <= q0));
             const float* lse2 = sLse + stage * BLK;
             const float* dlt = sDelta + stage * BLK;
+            const uint32_t* keepw = reinterpret_cast<const uint32_t*>(sKeep + stage * BLK) + q;   // word row/32 == q
+            const bool use_drop = p.drop_mask != nullptr;
             uint8_t* prow = sPT + row * 128;
             uint8_t* drow = sDST + row * 128;
 #pragma unroll 1
@@ -213,8 +222,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         if (!vis) s2 = masked_val;
                         pr = (kj < p.s && qi < p.s) ? exp2f(s2 - lse2[col]) : 0.f;
                     }
-                    pv[i] = pr;
-                    dv[i] = pr * (__uint_as_float(dr[i]) - dlt[col]) * p.scale;
+                    float dp = __uint_as_float(dr[i]);
+                    float pdrop = pr;
+                    if (use_drop) {   // dP flows back through the keep mask; dV sees the dropped probabilities
+                        const bool keep = (keepw[col * 4] >> lane) & 1u;
+                        dp = keep ? dp * p.drop_scale : 0.f;
+                        pdrop = keep ? pr * p.drop_scale : 0.f;
+                    }
+                    pv[i] = pdrop;
+                    dv[i] = pr * (dp - dlt[col]) * p.scale;
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {          // 4 chunks of 8 queries (16 bytes)
@@ -349,7 +365,9 @@ extern "C" int64_t cv_attn_bwd_workspace_bytes(int b, int heads, int head_dim, i
 extern "C" int cv_attn_bwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
                            const void* v, int64_t ldv, int64_t bsv, const void* out, const void* d_out,
                            const float* lse, void* dqkv, void* workspace, int b, int heads, int head_dim, int s,
-                           int sep, void* stream) {
+                           int sep, float dropout_p, const uint32_t* drop_mask, void* stream) {
+    CV_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout probability must be in [0, 1)");
+    CV_REQUIRE(dropout_p == 0.f || drop_mask != nullptr, "attention dropout needs the keep mask saved by the forward");
     CV_REQUIRE(q && k && v && out && d_out && lse && dqkv && workspace, "null pointer");
     CV_REQUIRE(head_dim == HD, "head_dim must be 64");
     CV_REQUIRE(b > 0 && heads > 0 && s > 0 && sep >= 0 && sep <= s, "bad sizes");
@@ -380,6 +398,8 @@ extern "C" int cv_attn_bwd(const void* q, int64_t ldq, int64_t bsq, const void* 
     p.scale_log2 = p.scale * LOG2E;
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+    p.drop_mask = dropout_p > 0.f ? drop_mask : nullptr;
+    p.drop_scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
     static bool attr_set = false;
     if (!attr_set) {
         CV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

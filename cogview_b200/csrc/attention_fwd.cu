@@ -46,8 +46,12 @@ struct AttnParams {
     int64_t ldo;        // row stride of out (elements)
     int64_t bso;        // batch stride of out (elements)
     float* lse;         // [b, heads, sq] natural-log LSE, or null
+    DropoutArgs drop;   // attention-probability dropout (mpu/sparse_transformer.py:667-669); p = 0 disables
+    uint32_t* drop_mask;// [b, heads, sq, nkb_all, 4]: keep bits of each (query, 128-key tile), saved for the backward
+    int nkb_all;        // ceil(sk / 128)
 };
 
+template <bool DROPOUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -193,6 +197,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float alpha = exp2f(m - mx);          // m = -inf on the first tile -> 0
             m = mx;
             float psum = 0.f;
+            uint32_t keep_bits[4] = {0u, 0u, 0u, 0u};
             uint8_t* prow = sP + (j & 1) * P_BYTES + row * 128;
 #pragma unroll
             for (int c = 0; c < BKV / 8; ++c) {         // 16 chunks of 8 keys (16 bytes)
@@ -206,10 +211,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pk);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) psum += __low2float(pb[t]) + __high2float(pb[t]);
+                if (DROPOUT) {   // dropout acts on the normalised probabilities: the row sum stays undropped
+                    const uint64_t ctr = ((((uint64_t)batch * p.heads + head) * p.sq + qi) * p.nkb_all + j) * 32 + c * 2;
+                    const uint4 r0 = philox4x32_10(p.drop.seed, ctr, p.drop.stream);
+                    const uint4 r1 = philox4x32_10(p.drop.seed, ctr + 1, p.drop.stream);
+                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const bool keep = rr[t] >= p.drop.threshold;
+                        bits |= (keep ? 1u : 0u) << t;
+                        e[t] = keep ? e[t] * p.drop.scale : 0.f;
+                    }
+                    keep_bits[c >> 2] |= bits << ((c & 3) * 8);
+                    pk.x = pack_bf16x2(e[0], e[1]); pk.y = pack_bf16x2(e[2], e[3]);
+                    pk.z = pack_bf16x2(e[4], e[5]); pk.w = pack_bf16x2(e[6], e[7]);
+                }
                 const int sub = c >> 3, cc = c & 7;     // sub-tile of 64 keys, 16-byte chunk within the 128 B row
                 *reinterpret_cast<uint4*>(prow + sub * (BQ * 128) + ((cc ^ (row & 7)) << 4)) = pk;
             }
             l = l * alpha + psum;
+            if (DROPOUT && qi < p.sq)
+                *reinterpret_cast<uint4*>(p.drop_mask + ((((size_t)batch * p.heads + head) * p.sq + qi) * p.nkb_all + j) * 4) =
+                    make_uint4(keep_bits[0], keep_bits[1], keep_bits[2], keep_bits[3]);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);
@@ -281,7 +305,10 @@ int encode_qkv_map(CUtensorMap* m, const void* base, int b, int s, int cols, int
 
 extern "C" int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
                            const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, float* lse,
-                           int b, int heads, int head_dim, int sq, int sk, int sep, void* stream) {
+                           int b, int heads, int head_dim, int sq, int sk, int sep, float dropout_p, uint64_t seed,
+                           uint32_t site, uint32_t* drop_mask, void* stream) {
+    CV_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout probability must be in [0, 1)");
+    CV_REQUIRE(dropout_p == 0.f || drop_mask != nullptr, "attention dropout needs the keep-mask buffer");
     CV_REQUIRE(q && k && v && out, "null pointer");
     CV_REQUIRE(head_dim == HD, "head_dim must be 64 (CogView: hidden / heads = 64)");
     CV_REQUIRE(b > 0 && heads > 0 && sq > 0 && sk >= sq, "need sk >= sq > 0");
@@ -305,13 +332,22 @@ extern "C" int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* 
     p.out = static_cast<__nv_bfloat16*>(out);
     p.ldo = ldo; p.bso = bso;
     p.lse = lse;
+    {
+        const cvh::HostDropout hd = cvh::make_dropout(dropout_p, seed, site);
+        p.drop.p = hd.p; p.drop.scale = hd.scale; p.drop.threshold = hd.threshold; p.drop.stream = hd.stream;
+        p.drop.seed = hd.seed;
+        p.drop_mask = drop_mask;
+        p.nkb_all = (sk + BKV - 1) / BKV;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     dim3 grid((sq + BQ - 1) / BQ, heads, b);
-    attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
+    if (dropout_p > 0.f) attn_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
+    else attn_fwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
     CV_LAUNCH_CHECK();
     return 0;
 }

@@ -80,6 +80,41 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Counter-based dropout (Philox4x32-10).  The keep-mask of element `idx` of dropout site `stream` is a pure
+// function of (seed, stream, idx): the forward kernel that applies the mask and the backward kernel that needs it
+// again regenerate it instead of storing it (torch.nn.Dropout of the reference: mpu/sparse_transformer.py:98,105,
+// 224,425 — bitwise parity with torch's generator is neither possible nor needed; parity runs use p = 0).
+// One call yields the random words of 4 consecutive elements (idx/4 is the counter).
+// ----------------------------------------------------------------------------------------------
+struct DropoutArgs {
+    float p;             // drop probability; 0 disables
+    float scale;         // 1 / (1 - p)
+    uint32_t threshold;  // keep iff random word >= threshold (= p * 2^32)
+    uint32_t stream;     // dropout site id
+    uint64_t seed;
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t counter, uint32_t stream) {
+    uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = stream, c3 = 0x9E3779B9u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// multiplies v[0..3] (elements idx4*4 .. idx4*4+3 of the site) by keep * scale
+__device__ __forceinline__ void dropout4(const DropoutArgs& d, uint64_t idx4, float& a, float& b, float& c, float& e) {
+    const uint4 r = philox4x32_10(d.seed, idx4, d.stream);
+    a = r.x >= d.threshold ? a * d.scale : 0.f;
+    b = r.y >= d.threshold ? b * d.scale : 0.f;
+    c = r.z >= d.threshold ? c * d.scale : 0.f;
+    e = r.w >= d.threshold ? e * d.scale : 0.f;
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -41,6 +41,7 @@ struct GemmParams {
     const __nv_bfloat16* aux;   // act == 3: pre-activation values [M, N] (leading dimension ldc)
     float* absmax;              // null or scalar: atomicMax |C| over valid entries
     int has_c2;                 // second bf16 output = pre-activation (bias added, no activation)
+    DropoutArgs drop;           // drop.p > 0: output dropout after bias/activation (element index m*N + n)
     void* c;                    // output [M, N] (bf16 or fp32), leading dimension ldc
     __nv_bfloat16* c2;          // optional pre-activation output (bf16, same ldc)
     int64_t ldc;
@@ -253,6 +254,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                 }
+                if (p.drop.p > 0.f) {
+#pragma unroll
+                    for (int g4 = 0; g4 < EPI_COLS / 4; ++g4) {
+                        const uint64_t idx4 = ((uint64_t)grow * p.N + ncol0 + g4 * 4) >> 2;
+                        dropout4(p.drop, idx4, v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                    }
+                }
                 if (row_ok) {
                     if (OUT_F32) {
                         float* dst = static_cast<float*>(p.c) + (size_t)grow * p.ldc + ncol0;
@@ -347,9 +355,9 @@ int dispatch(int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA, const CUte
 
 }  // namespace
 
-extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
-                            void* Cout, int c_is_f32, int64_t ldc, void* C2, const void* bias, int act, float* absmax,
-                            int M, int N, int K, int block_n, void* stream) {
+static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                     void* Cout, int c_is_f32, int64_t ldc, void* C2, const void* bias, int act, float* absmax,
+                     int M, int N, int K, int block_n, const cvh::HostDropout& hd, void* stream) {
     CV_REQUIRE(A && B && Cout, "null operand");
     CV_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
     CV_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
@@ -385,6 +393,10 @@ extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     p.bias = static_cast<const __nv_bfloat16*>(bias);
     p.act = act;
     p.absmax = absmax;
+    CV_REQUIRE(hd.p >= 0.f && hd.p < 1.f, "dropout probability must be in [0, 1)");
+    CV_REQUIRE(hd.p == 0.f || N % 4 == 0, "dropout needs N % 4 == 0");
+    p.drop.p = hd.p; p.drop.scale = hd.scale; p.drop.threshold = hd.threshold; p.drop.stream = hd.stream;
+    p.drop.seed = hd.seed;
     p.has_c2 = C2 != nullptr && act != 3;
     p.aux = act == 3 ? static_cast<const __nv_bfloat16*>(C2) : nullptr;
     p.c = Cout;
@@ -402,4 +414,19 @@ extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     if (rc) return rc;
     if (BN == 256) return dispatch<256>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, p, s);
     return dispatch<128>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, p, s);
+}
+
+extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                            void* Cout, int c_is_f32, int64_t ldc, void* C2, const void* bias, int act, float* absmax,
+                            int M, int N, int K, int block_n, void* stream) {
+    return gemm_impl(A, a_mn_major, lda, B, b_mn_major, ldb, Cout, c_is_f32, ldc, C2, bias, act, absmax, M, N, K,
+                     block_n, cvh::make_dropout(0.f, 0, 0), stream);
+}
+
+extern "C" int cv_gemm_bf16_dropout(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major,
+                                    int64_t ldb, void* Cout, int c_is_f32, int64_t ldc, void* C2, const void* bias,
+                                    int act, float* absmax, int M, int N, int K, int block_n, float dropout_p,
+                                    uint64_t seed, uint32_t site, void* stream) {
+    return gemm_impl(A, a_mn_major, lda, B, b_mn_major, ldb, Cout, c_is_f32, ldc, C2, bias, act, absmax, M, N, K,
+                     block_n, cvh::make_dropout(dropout_p, seed, site), stream);
 }

@@ -33,6 +33,23 @@ int fail_cu(const char* fn, CUresult r);                // driver error while en
         cvh::count_launches(1);                                \
     } while (0)
 
+// host-side description of a dropout site (see cv::DropoutArgs)
+struct HostDropout {
+    float p, scale;
+    uint32_t threshold, stream;
+    uint64_t seed;
+};
+inline HostDropout make_dropout(float p, uint64_t seed, uint32_t stream) {
+    HostDropout d;
+    d.p = p;
+    d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    double t = (double)p * 4294967296.0;
+    d.threshold = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    d.stream = stream;
+    d.seed = seed;
+    return d;
+}
+
 int num_sms();
 void count_launches(int n);
 long long launches();   // kernels launched by this library since load (cv_launch_count)

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(512)
 ln_bwd_fused_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const float* __restrict__ mean_in,
                     const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ gamma,
                     const float* __restrict__ dres, TDx* __restrict__ dx, float* __restrict__ partials, int rows,
-                    int cols, int rows_per_cta) {
+                    int cols, int rows_per_cta, const DropoutArgs drop) {
     __shared__ float red[2][16][2 * FB_R];          // [buffer][warp][s1 x R, s2 x R]
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,6 +221,10 @@ ln_bwd_fused_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const
                     const float4 q0 = ld4(dres + off + c0), q1 = ld4(dres + off + c1);
                     o0.x += q0.x; o0.y += q0.y; o0.z += q0.z; o0.w += q0.w;
                     o1.x += q1.x; o1.y += q1.y; o1.z += q1.z; o1.w += q1.w;
+                }
+                if (drop.p > 0.f) {   // x was the output of a dropout site: dx flows back through the same mask
+                    dropout4(drop, (off + c0) >> 2, o0.x, o0.y, o0.z, o0.w);
+                    dropout4(drop, (off + c1) >> 2, o1.x, o1.y, o1.z, o1.w);
                 }
                 st4(dx + off + c0, o0);
                 st4(dx + off + c1, o1);
@@ -316,7 +320,13 @@ extern "C" int64_t cv_layernorm_bwd_workspace_bytes(int rows, int cols) {
 extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16,
                                        const float* mean, const float* rstd, const void* gamma, const float* dres,
                                        void* dx, int dx_is_bf16, void* dgamma, void* dbeta, float* workspace,
-                                       int rows, int cols, void* stream) {
+                                       int rows, int cols, float dropout_p, uint64_t seed, uint32_t site,
+                                       void* stream) {
+    const cvh::HostDropout hd = cvh::make_dropout(dropout_p, seed, site);
+    DropoutArgs dargs;
+    dargs.p = hd.p; dargs.scale = hd.scale; dargs.threshold = hd.threshold; dargs.stream = hd.stream; dargs.seed = hd.seed;
+    CV_REQUIRE(dropout_p == 0.f || (cols % 256 == 0 && cols / 8 <= 512),
+               "dropout in the LayerNorm backward needs the fused path (hidden size % 256 == 0)");
     CV_REQUIRE(x && dy && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "null pointer");
     CV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -334,7 +344,7 @@ extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void*
 #define LAUNCH_F(TI, TDY, TDX)                                                                                 \
     ln_bwd_fused_kernel<TI, TDY, TDX><<<fgrid, threads, 0, s>>>(static_cast<const TI*>(x), static_cast<const TDY*>(dy), \
                                                                 mean, rstd, g, dres, static_cast<TDX*>(dx), workspace,   \
-                                                                rows, cols, rows_per_cta)
+                                                                rows, cols, rows_per_cta, dargs)
         if (x_is_bf16 && !dy_is_bf16 && dx_is_bf16) LAUNCH_F(__nv_bfloat16, float, __nv_bfloat16);
         else if (!x_is_bf16 && dy_is_bf16 && !dx_is_bf16) LAUNCH_F(float, __nv_bfloat16, float);
         else if (!x_is_bf16 && !dy_is_bf16 && !dx_is_bf16) LAUNCH_F(float, float, float);

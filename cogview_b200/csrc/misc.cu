@@ -15,7 +15,8 @@ using namespace cv;
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos,
                                  const __nv_bfloat16* __restrict__ wte, const __nv_bfloat16* __restrict__ wpe,
-                                 float* __restrict__ out, float* __restrict__ absmax, int rows, int h) {
+                                 float* __restrict__ out, float* __restrict__ absmax, int rows, int h,
+                                 const DropoutArgs drop) {
     pdl_launch_dependents();   // lets a PDL-launched consumer (decode path) start its prologue early
     const int warps_per_block = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -35,6 +36,11 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t*
                 v[2 * t] = __low2float(pa[t]) + __low2float(pb[t]);
                 v[2 * t + 1] = __high2float(pa[t]) + __high2float(pb[t]);
             }
+            if (drop.p > 0.f) {   // embedding dropout (mpu/sparse_transformer.py:524)
+                const uint64_t e = (uint64_t)r * h + i;
+                dropout4(drop, e >> 2, v[0], v[1], v[2], v[3]);
+                dropout4(drop, (e >> 2) + 1, v[4], v[5], v[6], v[7]);
+            }
             *reinterpret_cast<float4*>(o + i) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(o + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
 #pragma unroll
@@ -50,20 +56,37 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t*
 // dwte[ids[r]] += dx[r], dwpe[pos[r]] += dx[r]  (bf16 gradients, bf16x2 atomics)
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos,
                                  const float* __restrict__ dx, __nv_bfloat16* __restrict__ dwte,
-                                 __nv_bfloat16* __restrict__ dwpe, int rows, int h) {
+                                 __nv_bfloat16* __restrict__ dwpe, int rows, int h, const DropoutArgs drop) {
     const int warps_per_block = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = blockIdx.x * warps_per_block + warp; r < rows; r += gridDim.x * warps_per_block) {
         __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(dwte + (size_t)ids[r] * h);
         __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(dwpe + (size_t)pos[r] * h);
-        const float2* d = reinterpret_cast<const float2*>(dx + (size_t)r * h);
-        for (int i = lane; i < h / 2; i += 32) {
-            float2 v = d[i];
-            __nv_bfloat162 bv = __floats2bfloat162_rn(v.x, v.y);
-            atomicAdd(a + i, bv);
-            atomicAdd(b + i, bv);
+        const float4* d = reinterpret_cast<const float4*>(dx + (size_t)r * h);
+        for (int i = lane; i < h / 4; i += 32) {
+            float4 v = d[i];
+            if (drop.p > 0.f) dropout4(drop, ((uint64_t)r * h + 4 * (uint64_t)i) >> 2, v.x, v.y, v.z, v.w);
+            const __nv_bfloat162 b0 = __floats2bfloat162_rn(v.x, v.y), b1 = __floats2bfloat162_rn(v.z, v.w);
+            atomicAdd(a + 2 * i, b0); atomicAdd(a + 2 * i + 1, b1);
+            atomicAdd(b + 2 * i, b0); atomicAdd(b + 2 * i + 1, b1);
         }
     }
+}
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, size_t n, const DropoutArgs drop) {
+    for (size_t i4 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i4 * 4 < n; i4 += (size_t)gridDim.x * blockDim.x) {
+        float a = 1.f, b = 1.f, c = 1.f, e = 1.f;
+        dropout4(drop, i4, a, b, c, e);
+        const float v[4] = {a, b, c, e};
+        for (int t = 0; t < 4; ++t)
+            if (i4 * 4 + t < n) out[i4 * 4 + t] = v[t] != 0.f;
+    }
+}
+
+DropoutArgs to_dev(const cvh::HostDropout& hd) {
+    DropoutArgs d;
+    d.p = hd.p; d.scale = hd.scale; d.threshold = hd.threshold; d.stream = hd.stream; d.seed = hd.seed;
+    return d;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -243,8 +266,17 @@ int grid_for(size_t work_items, int threads) {
 
 }  // namespace
 
+extern "C" int cv_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
+    CV_REQUIRE(out && n > 0 && p >= 0.f && p < 1.f, "bad argument");
+    dropout_mask_kernel<<<grid_for((size_t)(n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        out, (size_t)n, to_dev(cvh::make_dropout(p, seed, site)));
+    CV_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int cv_embed_fwd(const int64_t* ids, const int64_t* pos, const void* wte, const void* wpe, float* out,
-                            float* absmax, int rows, int hidden, void* stream) {
+                            float* absmax, int rows, int hidden, float dropout_p, uint64_t seed, uint32_t site,
+                            void* stream) {
     CV_REQUIRE(ids && pos && wte && wpe && out, "null pointer");
     CV_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0, "hidden must be a multiple of 8");
     const int wpb = 8;
@@ -252,20 +284,21 @@ extern "C" int cv_embed_fwd(const int64_t* ids, const int64_t* pos, const void* 
     int cap = cvh::num_sms() * 4;
     embed_fwd_kernel<<<blocks < cap ? blocks : cap, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         ids, pos, static_cast<const __nv_bfloat16*>(wte), static_cast<const __nv_bfloat16*>(wpe), out, absmax, rows,
-        hidden);
+        hidden, to_dev(cvh::make_dropout(dropout_p, seed, site)));
     CV_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int cv_embed_bwd(const int64_t* ids, const int64_t* pos, const float* dx, void* dwte, void* dwpe, int rows,
-                            int hidden, void* stream) {
+                            int hidden, float dropout_p, uint64_t seed, uint32_t site, void* stream) {
     CV_REQUIRE(ids && pos && dx && dwte && dwpe, "null pointer");
-    CV_REQUIRE(rows > 0 && hidden > 0 && hidden % 2 == 0, "hidden must be even");
+    CV_REQUIRE(rows > 0 && hidden > 0 && hidden % 4 == 0, "hidden must be a multiple of 4");
     const int wpb = 8;
     int blocks = (rows + wpb - 1) / wpb;
     int cap = cvh::num_sms() * 4;
     embed_bwd_kernel<<<blocks < cap ? blocks : cap, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        ids, pos, dx, static_cast<__nv_bfloat16*>(dwte), static_cast<__nv_bfloat16*>(dwpe), rows, hidden);
+        ids, pos, dx, static_cast<__nv_bfloat16*>(dwte), static_cast<__nv_bfloat16*>(dwpe), rows, hidden,
+        to_dev(cvh::make_dropout(dropout_p, seed, site)));
     CV_LAUNCH_CHECK();
     return 0;
 }

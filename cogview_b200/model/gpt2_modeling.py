@@ -83,8 +83,6 @@ class GPT2Model(torch.nn.Module):
         if is_sparse == 1:
             raise NotImplementedError('sparse training (is_sparse=1) is not implemented in this round')
         tr = self.transformer
-        if tr.training and tr.embedding_dropout_prob > 0:
-            raise NotImplementedError('embedding dropout > 0 is not supported yet')
         b, sq = input_ids.shape
         mem_len = mems[0].size(1) if mems else 0
         sep = 0 if is_sparse == 2 else mask_to_sep(attention_mask, sq, sq + mem_len)
@@ -95,7 +93,8 @@ class GPT2Model(torch.nn.Module):
             return fast
         wte, wpe = self.word_embeddings.weight, tr.position_embeddings.weight
         if torch.is_grad_enabled() and (wte.requires_grad or wpe.requires_grad):
-            x, am_x = _EmbedFn.apply(input_ids, position_ids, wte, wpe)
+            p_emb = tr.embedding_dropout_prob if tr.training else 0.0
+            x, am_x = _EmbedFn.apply(input_ids, position_ids, wte, wpe, p_emb)
         else:
             am_x = ops.new_scalars(1, wte.device)
             x = ops.embed_fwd(input_ids, position_ids, _as_bf16(wte.detach()).contiguous(),

@@ -14,6 +14,25 @@ from .initialize import get_data_parallel_rank, get_model_parallel_rank
 _MODEL_PARALLEL_RNG_TRACKER_NAME = 'model-parallel-rng'
 _PARTITION_ACTIVATIONS = False
 
+# Dropout inside the fused kernels is counter-based: a site is (seed, site id); the keep mask is a pure function of
+# (seed, site id, element index), so forward, backward and a checkpoint recomputation regenerate identical masks.
+# The seed follows torch's default generator (set by set_random_seed -> torch.manual_seed); site ids count up.
+_DROPOUT_SITE = [0]
+
+
+def next_dropout_site():
+    """(seed, site id) for the next dropout site of this process."""
+    _DROPOUT_SITE[0] = (_DROPOUT_SITE[0] + 1) & 0xFFFFFFFF
+    return int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, _DROPOUT_SITE[0]
+
+
+def get_dropout_site_counter():
+    return _DROPOUT_SITE[0]
+
+
+def set_dropout_site_counter(v):
+    _DROPOUT_SITE[0] = int(v)
+
 
 def _get_state():
     return torch.cuda.get_rng_state() if torch.cuda.is_available() else torch.get_rng_state()
@@ -111,6 +130,7 @@ class CheckpointFunction(torch.autograd.Function):
         ctx.cpu_rng = torch.get_rng_state()
         ctx.dev_rng = _get_state()
         ctx.tracker_states = get_cuda_rng_tracker().get_states()
+        ctx.dropout_site = get_dropout_site_counter()
         ctx.tensor_idx = [i for i, a in enumerate(args) if torch.is_tensor(a)]
         ctx.other = {i: a for i, a in enumerate(args) if not torch.is_tensor(a)}
         ctx.nargs = len(args)
@@ -131,6 +151,8 @@ class CheckpointFunction(torch.autograd.Function):
             args[i] = a
         bwd_cpu, bwd_dev = torch.get_rng_state(), _get_state()
         bwd_tracker = get_cuda_rng_tracker().get_states()
+        bwd_site = get_dropout_site_counter()
+        set_dropout_site_counter(ctx.dropout_site)
         torch.set_rng_state(ctx.cpu_rng)
         _set_state(ctx.dev_rng)
         get_cuda_rng_tracker().set_states(ctx.tracker_states)
@@ -140,6 +162,7 @@ class CheckpointFunction(torch.autograd.Function):
         torch.set_rng_state(bwd_cpu)
         _set_state(bwd_dev)
         get_cuda_rng_tracker().set_states(bwd_tracker)
+        set_dropout_site_counter(bwd_site)
         if torch.is_tensor(outputs):
             outputs = (outputs,)
         pairs = [(o, g) for o, g in zip(outputs, grads) if torch.is_tensor(o) and o.requires_grad and g is not None]

@@ -21,7 +21,7 @@ import torch
 
 from .. import ops
 from .layers import ColumnParallelLinear, RowParallelLinear, _as_bf16
-from .random import checkpoint, get_cuda_rng_tracker  # noqa: F401  (API parity)
+from .random import checkpoint, get_cuda_rng_tracker, next_dropout_site  # noqa: F401
 from .utils import divide
 
 LN_EPS_DEFAULT = 1.0e-5
@@ -139,7 +139,7 @@ _PARAM_ORDER = ('input_layernorm.weight', 'input_layernorm.bias',
                 'fourth_layernorm.weight', 'fourth_layernorm.bias')
 
 
-def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None, attn=None):
+def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None, attn=None, drops=None):
     """One Sandwich-LN block (mpu/sparse_transformer.py:314-342) on the fp32 residual stream x [b*sq, h].
 
     am_x: 1-element fp32 tensor holding max|x|.  P: the 16 parameters in _PARAM_ORDER (bf16).
@@ -158,12 +158,20 @@ def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None, attn=N
         k, v = kv(k, v)
     if attn is not None:            # sparse inference: attention over a gathered key set
         ctx, lse = attn(q), None
+    elif training and drops is not None and drops['attn'][0] > 0:
+        ctx, lse, amask = ops.attn_fwd(q, k, v, heads, sep=sep, want_lse=True, dropout=drops['attn'])
+        drops['attn_mask'] = amask
     elif training:
         ctx, lse = ops.attn_fwd(q, k, v, heads, sep=sep, want_lse=True)
+    elif drops is not None and drops['attn'][0] > 0:   # forward only (checkpointed pass): same sites, masks not kept
+        ctx, _ = ops.attn_fwd(q, k, v, heads, sep=sep, dropout=drops['attn'])
+        lse = None
     else:
         ctx, lse = ops.attn_fwd(q, k, v, heads, sep=sep), None
     ctx2 = ctx.view(b * sq, h)
-    attn_out = ops.gemm(ctx2, wd, bias=bd, absmax=scal[0:1])
+    d_out_site = drops['out'] if drops is not None else None
+    d_mlp_site = drops['mlp'] if drops is not None else None
+    attn_out = ops.gemm(ctx2, wd, bias=bd, absmax=scal[0:1], dropout=d_out_site)
     y, mean3, rstd3 = ops.layernorm_absmax_fwd(attn_out, scal[0:1], g3, b3, eps, residual=x, out_dtype=torch.float32,
                                                absmax_out=scal[1:2], save_stats=training)
     ln2, mean2, rstd2 = ops.layernorm_absmax_fwd(y, scal[1:2], g2, b2, eps, save_stats=training)
@@ -171,7 +179,7 @@ def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None, attn=N
         h4, pre = ops.gemm(ln2, w1, bias=bb1, act=ops.ACT_GELU, want_preact=True)
     else:
         h4, pre = ops.gemm(ln2, w1, bias=bb1, act=ops.ACT_GELU), None
-    mlp_out = ops.gemm(h4, w2, bias=bb2, absmax=scal[2:3])
+    mlp_out = ops.gemm(h4, w2, bias=bb2, absmax=scal[2:3], dropout=d_mlp_site)
     out, mean4, rstd4 = ops.layernorm_absmax_fwd(mlp_out, scal[2:3], g4, b4, eps, residual=y, out_dtype=torch.float32,
                                                  absmax_out=scal[3:4], save_stats=training)
     if training:
@@ -180,7 +188,7 @@ def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None, attn=N
     return out, scal[3:4]
 
 
-def layer_backward(d_out, saved, P, heads, b, sq, sep):
+def layer_backward(d_out, saved, P, heads, b, sq, sep, drops=None):
     """Backward of layer_forward.  d_out: [b*sq, h] fp32.  Returns (d_x fp32, 16 parameter gradients bf16)."""
     (x, ln1, qkv, ctx, lse, attn_out, y, ln2, pre, h4, mlp_out,
      mean1, rstd1, mean2, rstd2, mean3, rstd3, mean4, rstd4) = saved
@@ -188,7 +196,8 @@ def layer_backward(d_out, saved, P, heads, b, sq, sep):
     h = x.shape[1]
     M = b * sq
     # out = y + LN4(mlp_out)
-    d_mlp_out, dg4, db4 = ops.layernorm_absmax_bwd(mlp_out, d_out, mean4, rstd4, g4, dx_dtype=torch.bfloat16)
+    d_mlp_out, dg4, db4 = ops.layernorm_absmax_bwd(mlp_out, d_out, mean4, rstd4, g4, dx_dtype=torch.bfloat16,
+                                                   dropout=drops['mlp'] if drops else None)
     d_pre = ops.gemm(d_mlp_out, w2, b_mn_major=True, act=ops.ACT_GELU_GRAD, aux=pre)   # (dY W2) * gelu'(pre)
     dw2 = ops.gemm(d_mlp_out, h4, a_mn_major=True, b_mn_major=True)
     dbb2 = ops.colsum(d_mlp_out)
@@ -197,14 +206,17 @@ def layer_backward(d_out, saved, P, heads, b, sq, sep):
     dbb1 = ops.colsum(d_pre)
     d_y, dg2, db2 = ops.layernorm_absmax_bwd(y, d_ln2, mean2, rstd2, g2, dres=d_out, dx_dtype=torch.float32)
     # y = x + LN3(attn_out)
-    d_attn_out, dg3, db3 = ops.layernorm_absmax_bwd(attn_out, d_y, mean3, rstd3, g3, dx_dtype=torch.bfloat16)
+    d_attn_out, dg3, db3 = ops.layernorm_absmax_bwd(attn_out, d_y, mean3, rstd3, g3, dx_dtype=torch.bfloat16,
+                                                    dropout=drops['out'] if drops else None)
     ctx2 = ctx.view(M, h)
     d_ctx = ops.gemm(d_attn_out, wd, b_mn_major=True)
     dwd = ops.gemm(d_attn_out, ctx2, a_mn_major=True, b_mn_major=True)
     dbd = ops.colsum(d_attn_out)
     qkv3 = qkv.view(b, sq, 3 * h)
+    use_ad = bool(drops) and drops['attn'][0] > 0
     d_qkv = ops.attn_bwd(qkv3[..., :h], qkv3[..., h:2 * h], qkv3[..., 2 * h:], ctx, d_ctx.view(b, sq, h), lse, heads,
-                         sep=sep)
+                         sep=sep, dropout_p=drops['attn'][0] if use_ad else 0.0,
+                         drop_mask=drops['attn_mask'] if use_ad else None)
     d_qkv2 = d_qkv.view(M, 3 * h)
     d_ln1 = ops.gemm(d_qkv2, wqkv, b_mn_major=True)
     dwqkv = ops.gemm(d_qkv2, ln1, a_mn_major=True, b_mn_major=True)
@@ -217,10 +229,19 @@ class _LayerFn(torch.autograd.Function):
     """autograd wrapper of layer_forward / layer_backward (training path, no memory)."""
 
     @staticmethod
-    def forward(ctx, x, am_x, heads, eps, b, sq, sep, *params):
+    def forward(ctx, x, am_x, heads, eps, b, sq, sep, p_attn, p_out, *params):
         P = tuple(_as_bf16(p) for p in params)
         save = []
-        out, am_out = layer_forward(x, am_x, P, heads, eps, b, sq, sep, save=save)
+        drops = None
+        if p_attn > 0 or p_out > 0:   # three dropout sites per layer: attention probs, attention output, MLP output
+            sa, so, sm = next_dropout_site(), next_dropout_site(), next_dropout_site()
+            drops = {'attn': (p_attn, sa[0], sa[1]), 'out': (p_out, so[0], so[1]), 'mlp': (p_out, sm[0], sm[1])}
+        out, am_out = layer_forward(x, am_x, P, heads, eps, b, sq, sep, save=save, drops=drops)
+        amask = drops.pop('attn_mask', None) if drops else None
+        ctx.drops = drops
+        ctx.has_amask = amask is not None
+        if amask is not None:
+            save.append(amask)
         ctx.save_for_backward(*save, *P)
         ctx.cfg = (heads, b, sq, sep, tuple(p.dtype for p in params))
         ctx.mark_non_differentiable(am_out)
@@ -231,9 +252,14 @@ class _LayerFn(torch.autograd.Function):
         heads, b, sq, sep, pdt = ctx.cfg
         saved = ctx.saved_tensors
         n = len(saved) - 16
-        d_x, grads = layer_backward(d_out.contiguous(), saved[:n], saved[n:], heads, b, sq, sep)
+        drops = ctx.drops
+        acts = saved[:n]
+        if ctx.has_amask:
+            drops = dict(drops, attn_mask=saved[n - 1])
+            acts = saved[:n - 1]
+        d_x, grads = layer_backward(d_out.contiguous(), acts, saved[n:], heads, b, sq, sep, drops=drops)
         grads = tuple(g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdt))
-        return (d_x, None, None, None, None, None, None) + grads
+        return (d_x, None, None, None, None, None, None, None, None) + grads
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -351,21 +377,25 @@ class GPT2ParallelTransformerLayer(torch.nn.Module):
         sd = dict(self.named_parameters())
         return [sd[n] for n in _PARAM_ORDER]
 
-    def _check_dropout(self):
-        if self.training and (self.attention_dropout_prob > 0 or self.output_dropout_prob > 0):
-            raise NotImplementedError('dropout > 0 in training mode is not supported by the fused layer yet; '
-                                      'construct the model with dropout probabilities 0 (parity runs do)')
-
     def fused_forward(self, x, am_x, b, sq, sep, kv=None, attn=None):
         """x: fp32 [b*sq, h] residual stream, am_x: max|x| scalar tensor -> (out, am_out)."""
-        self._check_dropout()
         params = self.param_list()
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
             if kv is not None:
                 raise NotImplementedError('training with memory is not supported')
-            return _LayerFn.apply(x, am_x, self.num_attention_heads, self.layernorm_epsilon, b, sq, sep, *params)
+            p_attn = self.attention_dropout_prob if self.training else 0.0
+            p_out = self.output_dropout_prob if self.training else 0.0
+            return _LayerFn.apply(x, am_x, self.num_attention_heads, self.layernorm_epsilon, b, sq, sep, p_attn, p_out,
+                                  *params)
+        drops = None
+        if self.training and (self.attention_dropout_prob > 0 or self.output_dropout_prob > 0):
+            # training-mode forward without autograd (the first pass of mpu.checkpoint): draw the same three sites
+            sa, so, sm = next_dropout_site(), next_dropout_site(), next_dropout_site()
+            drops = {'attn': (self.attention_dropout_prob, sa[0], sa[1]), 'out': (self.output_dropout_prob, so[0], so[1]),
+                     'mlp': (self.output_dropout_prob, sm[0], sm[1])}
         P = tuple(_as_bf16(p.detach()) for p in params)
-        return layer_forward(x, am_x, P, self.num_attention_heads, self.layernorm_epsilon, b, sq, sep, kv=kv, attn=attn)
+        return layer_forward(x, am_x, P, self.num_attention_heads, self.layernorm_epsilon, b, sq, sep, kv=kv, attn=attn,
+                             drops=drops)
 
     def forward(self, hidden_states, ltor_mask, pivot_idx=None, is_sparse=0, mem=None):
         """Reference signature: hidden_states [b, s, h], mask [1,1,s,s] or int sep; `mem` = hidden-state memory
@@ -413,10 +443,14 @@ class _EmbedFn(torch.autograd.Function):
     """hidden = wte[ids] + wpe[pos] as one gather kernel (fp32 out + its abs-max); scatter-add backward."""
 
     @staticmethod
-    def forward(ctx, ids, pos, wte, wpe):
+    def forward(ctx, ids, pos, wte, wpe, p_drop=0.0):
         am = ops.new_scalars(1, wte.device)
         wb, pb = _as_bf16(wte), _as_bf16(wpe)
-        out = ops.embed_fwd(ids, pos, wb.contiguous(), pb.contiguous(), am)
+        ctx.drop = None
+        if p_drop > 0:
+            seed, site = next_dropout_site()
+            ctx.drop = (p_drop, seed, site)
+        out = ops.embed_fwd(ids, pos, wb.contiguous(), pb.contiguous(), am, dropout=ctx.drop)
         ctx.save_for_backward(ids, pos)
         ctx.meta = (wte.shape, wpe.shape, wte.dtype, wpe.dtype, wte.device)
         ctx.mark_non_differentiable(am)
@@ -428,8 +462,8 @@ class _EmbedFn(torch.autograd.Function):
         ws, ps, wdt, pdt, dev = ctx.meta
         dwte = torch.zeros(ws, dtype=torch.bfloat16, device=dev)
         dwpe = torch.zeros(ps, dtype=torch.bfloat16, device=dev)
-        ops.embed_bwd(ids, pos, d_out.contiguous(), dwte, dwpe)
-        return None, None, dwte.to(wdt), dwpe.to(pdt)
+        ops.embed_bwd(ids, pos, d_out.contiguous(), dwte, dwpe, dropout=ctx.drop)
+        return None, None, dwte.to(wdt), dwpe.to(pdt), None
 
 
 class GPT2ParallelTransformer(torch.nn.Module):
@@ -561,10 +595,10 @@ class GPT2ParallelTransformer(torch.nn.Module):
         b, sq, h = hidden_states.shape
         mem_len = mems[0].size(1) if mems else 0
         sep = 0 if is_sparse == 2 else mask_to_sep(attention_mask, sq, sq + mem_len)
-        if self.training and self.embedding_dropout_prob > 0:
-            raise NotImplementedError('embedding dropout > 0 is not supported yet')
         pe = torch.nn.functional.embedding(position_ids, self.position_embeddings.weight)
         x = (hidden_states.float() + pe.float()).reshape(b * sq, h).contiguous()
+        if self.training and self.embedding_dropout_prob > 0:
+            x = torch.nn.functional.dropout(x, self.embedding_dropout_prob)   # standalone entry (GPT2Model fuses it)
         am_x = ops.absmax(x.detach())
         y, mem_layers = self.run_layers(x, am_x, b, sq, sep, mems, is_sparse=is_sparse,
                                         txt_indices_bool=txt_indices_bool, img_indices_bool=img_indices_bool)

@@ -15,7 +15,7 @@ ACT_GELU_GRAD = 3   # multiply the result by gelu'(aux) (GELU backward fused int
 
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, bias=None, act=ACT_NONE, out_dtype=torch.bfloat16,
-         absmax=None, want_preact=False, out=None, block_n=0, aux=None):
+         absmax=None, want_preact=False, out=None, block_n=0, aux=None, dropout=None):
     """C[M,N] = op(A)[M,K] @ op(B)[N,K]^T (+bias) (+GELU).
 
     a: [M,K] (or [K,M] when a_mn_major); b: [N,K] (or [K,N] when b_mn_major); both bf16, last dim contiguous.
@@ -44,9 +44,15 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, bias=None, act=ACT_NONE, o
         pre = aux
     if bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.numel() == N
-    rc = lib().cv_gemm_bf16(ptr(a), int(a_mn_major), a.stride(0), ptr(b), int(b_mn_major), b.stride(0),
-                            ptr(out), int(out.dtype == torch.float32), out.stride(0), ptr(pre), ptr(bias), int(act),
-                            ptr(absmax), M, N, K, block_n, stream_ptr())
+    if dropout is not None and dropout[0] > 0:
+        rc = lib().cv_gemm_bf16_dropout(ptr(a), int(a_mn_major), a.stride(0), ptr(b), int(b_mn_major), b.stride(0),
+                                        ptr(out), int(out.dtype == torch.float32), out.stride(0), ptr(pre), ptr(bias),
+                                        int(act), ptr(absmax), M, N, K, block_n, float(dropout[0]), int(dropout[1]),
+                                        int(dropout[2]), stream_ptr())
+    else:
+        rc = lib().cv_gemm_bf16(ptr(a), int(a_mn_major), a.stride(0), ptr(b), int(b_mn_major), b.stride(0),
+                                ptr(out), int(out.dtype == torch.float32), out.stride(0), ptr(pre), ptr(bias), int(act),
+                                ptr(absmax), M, N, K, block_n, stream_ptr())
     check(rc, "cv_gemm_bf16")
     return (out, pre) if want_preact else out
 
@@ -90,7 +96,20 @@ def layernorm_absmax_fwd(x, absmax_in, gamma, beta, eps, *, residual=None, out_d
     return out, mean, rstd
 
 
-def layernorm_absmax_bwd(x, dy, mean, rstd, gamma, *, dres=None, dx_dtype=torch.float32):
+def _drop3(dropout):
+    if dropout is None or dropout[0] <= 0:
+        return 0.0, 0, 0
+    return float(dropout[0]), int(dropout[1]), int(dropout[2])
+
+
+def dropout_mask(n, p, seed, site, device="cuda"):
+    """Keep mask (uint8) of the first n elements of dropout site (seed, site) — what every fused dropout uses."""
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    check(lib().cv_dropout_mask(ptr(out), n, float(p), int(seed), int(site), stream_ptr()), "cv_dropout_mask")
+    return out
+
+
+def layernorm_absmax_bwd(x, dy, mean, rstd, gamma, *, dres=None, dx_dtype=torch.float32, dropout=None):
     """Returns (dx, dgamma, dbeta)."""
     require_cuda(x, dy, mean, rstd, gamma, dres)
     assert x.is_contiguous() and dy.is_contiguous()
@@ -104,7 +123,7 @@ def layernorm_absmax_bwd(x, dy, mean, rstd, gamma, *, dres=None, dx_dtype=torch.
     rc = lib().cv_layernorm_absmax_bwd(ptr(x), int(x.dtype == torch.bfloat16), ptr(dy),
                                        int(dy.dtype == torch.bfloat16), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres),
                                        ptr(dx), int(dx_dtype == torch.bfloat16), ptr(dgamma), ptr(dbeta), ptr(ws),
-                                       rows, cols, stream_ptr())
+                                       rows, cols, *_drop3(dropout), stream_ptr())
     check(rc, "cv_layernorm_absmax_bwd")
     return dx, dgamma, dbeta
 
@@ -112,9 +131,9 @@ def layernorm_absmax_bwd(x, dy, mean, rstd, gamma, *, dres=None, dx_dtype=torch.
 # ----------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------
-def attn_fwd(q, k, v, heads, *, sep=0, want_lse=False):
+def attn_fwd(q, k, v, heads, *, sep=0, want_lse=False, dropout=None):
     """q: [b, sq, heads*64] view, k/v: [b, sk, heads*64] views (last dim contiguous, bf16).
-    Returns ctx [b, sq, heads*64] bf16 (and lse [b, heads, sq] fp32)."""
+    Returns ctx [b, sq, heads*64] bf16 (and lse [b, heads, sq] fp32; and the keep-bit tensor when dropout is on)."""
     require_cuda(q, k, v)
     b, sq, hq = q.shape
     sk = k.shape[1]
@@ -122,14 +141,20 @@ def attn_fwd(q, k, v, heads, *, sep=0, want_lse=False):
     assert hq == heads * 64 and k.shape[2] == hq and v.shape == k.shape
     out = torch.empty((b, sq, hq), dtype=torch.bfloat16, device=q.device)
     lse = torch.empty((b, heads, sq), dtype=torch.float32, device=q.device) if want_lse else None
+    dp, dseed, dsite = _drop3(dropout)
+    mask = None
+    if dp > 0:
+        mask = torch.empty((b, heads, sq, (sk + 127) // 128, 4), dtype=torch.int32, device=q.device)
     rc = lib().cv_attn_fwd(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
                            v.stride(0), ptr(out), out.stride(1), out.stride(0), ptr(lse), b, heads, 64, sq, sk,
-                           int(sep), stream_ptr())
+                           int(sep), dp, dseed, dsite, ptr(mask), stream_ptr())
     check(rc, "cv_attn_fwd")
+    if dp > 0:
+        return (out, lse, mask) if want_lse else (out, mask)
     return (out, lse) if want_lse else out
 
 
-def attn_bwd(q, k, v, out, d_out, lse, heads, *, sep=0):
+def attn_bwd(q, k, v, out, d_out, lse, heads, *, sep=0, dropout_p=0.0, drop_mask=None):
     """Backward of attn_fwd for sq == sk.  Returns dqkv [b, s, 3*heads*64] bf16 (dQ | dK | dV)."""
     require_cuda(q, k, v, out, d_out, lse)
     b, s, h = q.shape
@@ -139,7 +164,7 @@ def attn_bwd(q, k, v, out, d_out, lse, heads, *, sep=0):
     ws = torch.empty(lib().cv_attn_bwd_workspace_bytes(b, heads, 64, s) // 4, dtype=torch.float32, device=q.device)
     rc = lib().cv_attn_bwd(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
                            v.stride(0), ptr(out), ptr(d_out), ptr(lse), ptr(dqkv), ptr(ws), b, heads, 64, s, int(sep),
-                           stream_ptr())
+                           float(dropout_p), ptr(drop_mask), stream_ptr())
     check(rc, "cv_attn_bwd")
     return dqkv
 
@@ -147,7 +172,7 @@ def attn_bwd(q, k, v, out, d_out, lse, heads, *, sep=0):
 # ----------------------------------------------------------------------------------------------------
 # embedding, cross-entropy, small backward helpers
 # ----------------------------------------------------------------------------------------------------
-def embed_fwd(ids, pos, wte, wpe, absmax_out=None):
+def embed_fwd(ids, pos, wte, wpe, absmax_out=None, dropout=None):
     require_cuda(ids, pos, wte, wpe)
     ids = ids.contiguous().view(-1)
     pos = pos.contiguous().view(-1)
@@ -156,18 +181,18 @@ def embed_fwd(ids, pos, wte, wpe, absmax_out=None):
     h = wte.shape[1]
     out = torch.empty((ids.numel(), h), dtype=torch.float32, device=wte.device)
     check(lib().cv_embed_fwd(ptr(ids), ptr(pos), ptr(wte), ptr(wpe), ptr(out), ptr(absmax_out), ids.numel(), h,
-                             stream_ptr()), "cv_embed_fwd")
+                             *_drop3(dropout), stream_ptr()), "cv_embed_fwd")
     return out
 
 
-def embed_bwd(ids, pos, dx, dwte, dwpe):
+def embed_bwd(ids, pos, dx, dwte, dwpe, dropout=None):
     """Accumulates into dwte / dwpe (bf16, contiguous)."""
     require_cuda(ids, pos, dx, dwte, dwpe)
     ids = ids.contiguous().view(-1)
     pos = pos.contiguous().view(-1)
     assert dx.dtype == torch.float32 and dx.is_contiguous()
     check(lib().cv_embed_bwd(ptr(ids), ptr(pos), ptr(dx), ptr(dwte), ptr(dwpe), ids.numel(), dwte.shape[1],
-                             stream_ptr()), "cv_embed_bwd")
+                             *_drop3(dropout), stream_ptr()), "cv_embed_bwd")
 
 
 def cross_entropy_fwd(logits, target):

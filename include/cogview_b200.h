@@ -46,6 +46,13 @@ long long cv_launch_count(void);
 int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
                  void* C, int c_is_f32, int64_t ldc, void* C2, const void* bias, int act, float* absmax,
                  int M, int N, int K, int block_n, void* stream);
+/* same, with output dropout fused after bias/activation (output_dropout of mpu/sparse_transformer.py:167 and :233):
+ * element (m, n) is kept iff the counter-based generator of site (seed, site) says so, kept values are scaled by
+ * 1/(1-p); abs-max is taken after the dropout.  N % 4 == 0. */
+int cv_gemm_bf16_dropout(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                         void* C, int c_is_f32, int64_t ldc, void* C2, const void* bias, int act, float* absmax,
+                         int M, int N, int K, int block_n, float dropout_p, uint64_t seed, uint32_t site,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Abs-max pre-scaled LayerNorm: y = LN(x / (max|x|/8)) * gamma + beta (+ residual)
@@ -62,9 +69,11 @@ int cv_layernorm_absmax_fwd(const void* x, int x_is_bf16, const float* absmax_in
 int64_t cv_layernorm_bwd_workspace_bytes(int rows, int cols);
 /* dx = LN'(dy) (+ dres); dgamma/dbeta bf16 [cols]; workspace of cv_layernorm_bwd_workspace_bytes() bytes.
  * The abs-max scale is a detached constant in the reference (x.abs().max().detach()), and so it is here. */
+/* dropout_p > 0: x was the output of dropout site (seed, site) — dx is multiplied by that site's keep mask / (1-p). */
 int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, const float* mean,
                             const float* rstd, const void* gamma, const float* dres, void* dx, int dx_is_bf16,
-                            void* dgamma, void* dbeta, float* workspace, int rows, int cols, void* stream);
+                            void* dgamma, void* dbeta, float* workspace, int rows, int cols, float dropout_p,
+                            uint64_t seed, uint32_t site, void* stream);
 int cv_absmax(const void* x, int x_is_bf16, int64_t n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -77,10 +86,14 @@ int cv_absmax(const void* x, int x_is_bf16, int64_t n, float* out, void* stream)
  *         (sep = 0: lower-triangular mask of pretrain_gpt2.py:218-221; sep > 0: the int-`sep` form of
  *          mpu/sparse_transformer.py:477-489)
  *   out: [b, sq, heads*64] bf16 (token-major, what the out-projection GEMM reads); lse: NULL or [b, heads, sq]
+ *   dropout_p > 0: dropout on the attention probabilities (torch.nn.Dropout under the RNG-tracker fork,
+ *         mpu/sparse_transformer.py:667-669) from the counter-based generator (seed, site); drop_mask
+ *         [b, heads, sq, ceil(sk/128), 4] uint32 receives the keep bits for the backward.
  * ---------------------------------------------------------------------------------------------- */
 int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
                 int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, float* lse, int b, int heads,
-                int head_dim, int sq, int sk, int sep, void* stream);
+                int head_dim, int sq, int sk, int sep, float dropout_p, uint64_t seed, uint32_t site,
+                uint32_t* drop_mask, void* stream);
 
 /* Backward of cv_attn_fwd for sq == sk (training).  q/k/v as in cv_attn_fwd; out, d_out: [b, s, heads*64] bf16
  * contiguous; lse from the forward.  dqkv: [b, s, 3*heads*64] bf16 (dQ | dK | dV, the layout of the packed QKV
@@ -88,16 +101,20 @@ int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t 
 int64_t cv_attn_bwd_workspace_bytes(int b, int heads, int head_dim, int s);
 int cv_attn_bwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
                 int64_t ldv, int64_t bsv, const void* out, const void* d_out, const float* lse, void* dqkv,
-                void* workspace, int b, int heads, int head_dim, int s, int sep, void* stream);
+                void* workspace, int b, int heads, int head_dim, int s, int sep, float dropout_p,
+                const uint32_t* drop_mask, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding: hidden = wte[ids] + wpe[pos] (fp32) and max|hidden|
  *   replaces VocabParallelEmbedding.forward (mpu/layers.py:117-133) + position add (mpu/sparse_transformer.py:522-523)
  * ---------------------------------------------------------------------------------------------- */
 int cv_embed_fwd(const int64_t* ids, const int64_t* pos, const void* wte, const void* wpe, float* out,
-                 float* absmax, int rows, int hidden, void* stream);
+                 float* absmax, int rows, int hidden, float dropout_p, uint64_t seed, uint32_t site, void* stream);
 int cv_embed_bwd(const int64_t* ids, const int64_t* pos, const float* dx, void* dwte, void* dwpe, int rows,
-                 int hidden, void* stream);
+                 int hidden, float dropout_p, uint64_t seed, uint32_t site, void* stream);
+/* keep mask (1 = kept) of the first n elements of dropout site (seed, site) — the pure function of
+ * (seed, site, element index) that every fused dropout in this library uses; exposed for tests. */
+int cv_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Vocab cross-entropy on fp32 logits — mpu/cross_entropy.py:27-104 at model-parallel size 1.
