@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--gen-tokens", type=int, default=1024)
     ap.add_argument("--model", default="4b", choices=["4b", "tiny"])
     ap.add_argument("--train-steps", type=int, default=None)
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="embedding/attention/hidden dropout of the training workload (reference scripts: 0.1)")
     return ap.parse_args()
 
 
@@ -98,7 +100,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # model / workload construction
 # ----------------------------------------------------------------------------------------------------
-def build_model(cfg, max_memory_length, device):
+def build_model(cfg, max_memory_length, device, dropout=0.0):
     from cogview_b200.model import GPT2Model
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
@@ -106,9 +108,9 @@ def build_model(cfg, max_memory_length, device):
         with torch.device(device):
             model = GPT2Model(num_layers=cfg["num_layers"], vocab_size=cfg["vocab_size"],
                               hidden_size=cfg["hidden_size"], num_attention_heads=cfg["num_attention_heads"],
-                              embedding_dropout_prob=0.0, attention_dropout_prob=0.0, output_dropout_prob=0.0,
-                              max_sequence_length=cfg["max_sequence_length"], max_memory_length=max_memory_length,
-                              checkpoint_activations=False)
+                              embedding_dropout_prob=dropout, attention_dropout_prob=dropout,
+                              output_dropout_prob=dropout, max_sequence_length=cfg["max_sequence_length"],
+                              max_memory_length=max_memory_length, checkpoint_activations=False)
     finally:
         torch.set_default_dtype(old)
     return model
@@ -270,7 +272,7 @@ def run_train(args, cfg, world, rank, dev_index, steps, warmup):
     from cogview_b200 import mpu
     from cogview_b200.model import (PyTorchDistributedDataParallel, gpt2_get_params_for_weight_decay_optimization)
     from cogview_b200.optim import FusedAdamW
-    model = build_model(cfg, 0, "cuda").train()
+    model = build_model(cfg, 0, "cuda", dropout=args.dropout).train()
     groups = gpt2_get_params_for_weight_decay_optimization(model)
     for g in groups:
         g.setdefault("weight_decay", 0.01)
@@ -324,8 +326,9 @@ def run_train(args, cfg, world, rank, dev_index, steps, warmup):
                e2e=dict(value=tokens_per_step * steps / (ms_e2e / 1e3), unit="tokens/s",
                         h2d_bytes_per_step=int(host_tokens.numel() * 8), d2h_bytes_per_step=4),
                gpu_launches=int(n_launch / max(1, steps + warmup)) * steps,
-               config=dict(workload="configs[2]: 4B training step, bf16, %d x %d tokens per GPU, dropout 0, AdamW + clip 1.0, "
-                                    "no activation recompute" % (b, s), global_batch=b * world,
+               config=dict(workload="configs[2]: 4B training step, bf16, %d x %d tokens per GPU, dropout %.2f (embedding, "
+                                    "attention, hidden), AdamW + clip 1.0, no activation recompute" % (b, s, args.dropout),
+                           global_batch=b * world,
                            parallelism="dp%d" % world),
                step_flops_per_gpu=flops_per_token * tokens_per_step / world,
                roofline_step=dict(bound="tensor", achieved=achieved, peak=pk["tf_sust"], unit="TFLOP/s",

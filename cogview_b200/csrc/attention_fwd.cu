@@ -212,14 +212,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int t = 0; t < 4; ++t) psum += __low2float(pb[t]) + __high2float(pb[t]);
                 if (DROPOUT) {   // dropout acts on the normalised probabilities: the row sum stays undropped
-                    const uint64_t ctr = ((((uint64_t)batch * p.heads + head) * p.sq + qi) * p.nkb_all + j) * 32 + c * 2;
+                    // one Philox call per 8 keys: eight 16-bit uniforms against a 16-bit threshold (p to within 2^-16)
+                    const uint64_t ctr = ((((uint64_t)batch * p.heads + head) * p.sq + qi) * p.nkb_all + j) * 16 + c;
                     const uint4 r0 = philox4x32_10(p.drop.seed, ctr, p.drop.stream);
-                    const uint4 r1 = philox4x32_10(p.drop.seed, ctr + 1, p.drop.stream);
-                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    const uint32_t thr16 = p.drop.threshold >> 16;
+                    const uint32_t rr[8] = {r0.x & 0xffffu, r0.x >> 16, r0.y & 0xffffu, r0.y >> 16,
+                                            r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
                     uint32_t bits = 0;
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
-                        const bool keep = rr[t] >= p.drop.threshold;
+                        const bool keep = rr[t] >= thr16;
                         bits |= (keep ? 1u : 0u) << t;
                         e[t] = keep ? e[t] * p.drop.scale : 0.f;
                     }
