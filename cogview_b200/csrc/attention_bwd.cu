@@ -146,6 +146,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tc_fence_after();
                 const uint32_t q_addr = smem_u32(sQDO + stage * 2 * TILE_BYTES);
                 const uint32_t do_addr = q_addr + TILE_BYTES;
+                // dQ first: the softmax warps are waiting for it, and its read-out (TMEM -> red.add) then overlaps dV / dK
+#pragma unroll
+                for (int k = 0; k < BLK / 16; ++k)     // reduction over the 128 keys of this block
+                    umma_f16(tmem_base + TM_DQ, make_smem_desc_sw128(dst_addr + k * 2048, BLK * 128, 1024),
+                             make_smem_desc_sw128(k_addr + k * 2048, BLK * 128, 1024), idesc_dq, k != 0);
+                umma_commit(dq_full);
 #pragma unroll
                 for (int k = 0; k < BLK / 16; ++k) {   // reduction over the 128 queries of this tile
                     const uint32_t a_off = (k >> 2) * (BLK * 128) + (k & 3) * 32;
@@ -154,13 +160,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     umma_f16(tmem_base + TM_DK, make_smem_desc_sw128(dst_addr + a_off, 0, 1024),
                              make_smem_desc_sw128(q_addr + k * 2048, BLK * 128, 1024), idesc_acc, (t | k) != 0);
                 }
-#pragma unroll
-                for (int k = 0; k < BLK / 16; ++k)     // reduction over the 128 keys of this block
-                    umma_f16(tmem_base + TM_DQ, make_smem_desc_sw128(dst_addr + k * 2048, BLK * 128, 1024),
-                             make_smem_desc_sw128(k_addr + k * 2048, BLK * 128, 1024), idesc_dq, k != 0);
                 umma_commit(&qdo_empty[stage]);
                 umma_commit(pds_free);
-                umma_commit(dq_full);
                 if (++stage == QDO_STAGES) { stage = 0; phase ^= 1; }
                 if (t + 1 < ntiles) {
                     mbar_wait(&qdo_full[stage], phase);
@@ -178,17 +179,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float masked_val = -10000.0f * LOG2E;
         const size_t stat_base = ((size_t)batch * p.heads + head) * p.s;
         int stage = 0;
+        float pre_lse, pre_delta;
+        uint4 pre_keep = make_uint4(0, 0, 0, 0);
+        {
+            const int qn = i_start * BLK + epi_tid;
+            pre_lse = (qn < p.s) ? p.lse[stat_base + qn] * LOG2E : 0.f;
+            pre_delta = (qn < p.s) ? p.delta[stat_base + qn] : 0.f;
+            if (p.drop_mask != nullptr && qn < p.s)
+                pre_keep = *reinterpret_cast<const uint4*>(p.drop_mask + ((stat_base + qn) * (size_t)nqb + kb) * 4);
+        }
         for (int t = 0; t < ntiles; ++t) {
             const int q0 = (i_start + t) * BLK;
-            // stage lse (log2 domain) and delta of this query block
-            {
-                const int qi = q0 + epi_tid;
-                sLse[stage * BLK + epi_tid] = (qi < p.s) ? p.lse[stat_base + qi] * LOG2E : 0.f;
-                sDelta[stage * BLK + epi_tid] = (qi < p.s) ? p.delta[stat_base + qi] : 0.f;
+            // lse (log2 domain), delta and keep bits of this query block were fetched one tile ahead (registers):
+            // publish them, then start the fetch for the next tile so its global-load latency is off the critical path
+            sLse[stage * BLK + epi_tid] = pre_lse;
+            sDelta[stage * BLK + epi_tid] = pre_delta;
+            if (p.drop_mask != nullptr) sKeep[stage * BLK + epi_tid] = pre_keep;
+            if (t + 1 < ntiles) {
+                const int qn = q0 + BLK + epi_tid;
+                pre_lse = (qn < p.s) ? p.lse[stat_base + qn] * LOG2E : 0.f;
+                pre_delta = (qn < p.s) ? p.delta[stat_base + qn] : 0.f;
                 if (p.drop_mask != nullptr)
-                    sKeep[stage * BLK + epi_tid] = (qi < p.s)
-                        ? *reinterpret_cast<const uint4*>(p.drop_mask + ((stat_base + qi) * (size_t)nqb + kb) * 4)
-                        : make_uint4(0, 0, 0, 0);
+                    pre_keep = (qn < p.s) ? *reinterpret_cast<const uint4*>(p.drop_mask + ((stat_base + qn) * (size_t)nqb + kb) * 4)
+                                          : make_uint4(0, 0, 0, 0);
             }
             named_bar_sync(1, 128);
             mbar_wait(sdp_full, t & 1);
@@ -272,7 +285,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             if (++stage == QDO_STAGES) stage = 0;
         }
-        // dK / dV of this key block (complete once the last tile's MMAs retired: dq_full of the last tile)
+        // dK / dV of this key block: complete once the last tile's dV / dK MMAs retired (its pds_free commit)
+        mbar_wait(pds_free, (ntiles - 1) & 1);
+        tc_fence_after();
         // (tcgen05.ld is warp-collective: every lane loads, only in-range rows store)
         {
             const int H3 = 3 * p.heads * HD;
