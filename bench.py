@@ -49,6 +49,14 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -260,7 +268,9 @@ def sample_roofline(model, nb, ms_per_step, gen_tokens):
                  for w, b in mats)
     achieved = nbytes / (ms / 1e3) / 1e9
     return dict(kernel="linear_small_m_kernel", bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s",
-                frac=achieved / pk["hbm"], traffic=None, peak_source=pk["src"], launches_per_step=len(mats),
+                frac=achieved / pk["hbm"], traffic=measured_traffic("linear_small_m_kernel"),
+                traffic_note="ncu capture of the four per-layer shapes (profiles/r01_traffic.json): 1.001x algorithmic",
+                peak_source=pk["src"], launches_per_step=len(mats),
                 bytes_per_launch=nbytes / len(mats), avg_launch_us=ms * 1e3 / len(mats),
                 share_of_step=ms / (ms_per_step / gen_tokens), note="share_of_step = linear sweep / one decode step")
 
@@ -370,7 +380,9 @@ def gemm_roofline(cfg, M):
         del ws, x
     achieved = tot_f / tot_ms / 1e9
     return dict(kernel="gemm_kernel", bound="tensor", achieved=achieved, peak=pk["tf_burst"], unit="TFLOP/s",
-                frac=achieved / pk["tf_burst"], traffic=None, peak_source=pk["src"], shapes=out,
+                frac=achieved / pk["tf_burst"], traffic=measured_traffic("gemm_kernel"),
+                traffic_note="ncu capture of the qkv shape (profiles/r01_traffic.json): operands read once",
+                peak_source=pk["src"], shapes=out,
                 flops_per_launch=tot_f / n, avg_launch_us=tot_ms * 1e3 / n)
 
 

@@ -215,35 +215,45 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool use_drop = p.drop_mask != nullptr;
             uint8_t* prow = sPT + row * 128;
             uint8_t* drow = sDST + row * 128;
-#pragma unroll 1
+#pragma unroll 2
             for (int c = 0; c < BLK / 32; ++c) {
                 uint32_t sr[32], dr[32];
                 tmem_ld_x32(lane_addr + TM_ST + c * 32, sr);
                 tmem_ld_x32(lane_addr + TM_DPT + c * 32, dr);
                 tmem_ld_wait();
                 float pv[32], dv[32];
+                if (full_vis && !use_drop) {           // interior tile, no dropout: branch-free inner loop
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int col = c * 32 + i;
-                    const int qi = q0 + col;
-                    float s2 = __uint_as_float(sr[i]) * p.scale_log2;
-                    float pr;
-                    if (full_vis) {
-                        pr = exp2f(s2 - lse2[col]);
-                    } else {
-                        const bool vis = (kj < p.sep_eff) || (kj <= qi);
-                        if (!vis) s2 = masked_val;
-                        pr = (kj < p.s && qi < p.s) ? exp2f(s2 - lse2[col]) : 0.f;
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c * 32 + i;
+                        const float pr = exp2f(__uint_as_float(sr[i]) * p.scale_log2 - lse2[col]);
+                        pv[i] = pr;
+                        dv[i] = pr * (__uint_as_float(dr[i]) - dlt[col]) * p.scale;
                     }
-                    float dp = __uint_as_float(dr[i]);
-                    float pdrop = pr;
-                    if (use_drop) {   // dP flows back through the keep mask; dV sees the dropped probabilities
-                        const bool keep = (keepw[col * 4] >> lane) & 1u;
-                        dp = keep ? dp * p.drop_scale : 0.f;
-                        pdrop = keep ? pr * p.drop_scale : 0.f;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c * 32 + i;
+                        const int qi = q0 + col;
+                        float s2 = __uint_as_float(sr[i]) * p.scale_log2;
+                        float pr;
+                        if (full_vis) {
+                            pr = exp2f(s2 - lse2[col]);
+                        } else {
+                            const bool vis = (kj < p.sep_eff) || (kj <= qi);
+                            if (!vis) s2 = masked_val;
+                            pr = (kj < p.s && qi < p.s) ? exp2f(s2 - lse2[col]) : 0.f;
+                        }
+                        float dp = __uint_as_float(dr[i]);
+                        float pdrop = pr;
+                        if (use_drop) {   // dP flows back through the keep mask; dV sees the dropped probabilities
+                            const bool keep = (keepw[col * 4] >> lane) & 1u;
+                            dp = keep ? dp * p.drop_scale : 0.f;
+                            pdrop = keep ? pr * p.drop_scale : 0.f;
+                        }
+                        pv[i] = pdrop;
+                        dv[i] = pr * (dp - dlt[col]) * p.scale;
                     }
-                    pv[i] = pdrop;
-                    dv[i] = pr * (dp - dlt[col]) * p.scale;
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {          // 4 chunks of 8 queries (16 bytes)
