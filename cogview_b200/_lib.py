@@ -33,7 +33,7 @@ def _declare(lib):
     U64, U32 = ctypes.c_uint64, ctypes.c_uint32
     sigs.update({
         "cv_layernorm_absmax_fwd": [P, I, P, P, P, F, P, P, I, P, P, P, I, I, P],
-        "cv_layernorm_absmax_bwd": [P, I, P, I, P, P, P, P, P, I, P, P, P, I, I, F, U64, U32, P],
+        "cv_layernorm_absmax_bwd": [P, I, P, I, P, P, P, P, P, I, P, P, P, I, I, F, U64, U32, P, P],
         "cv_absmax": [P, I, L, P, P],
         "cv_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, F, U64, U32, P, P],
         "cv_attn_bwd": [P, L, L, P, L, L, P, L, L, P, P, P, P, P, I, I, I, I, I, F, P, P],
@@ -43,6 +43,8 @@ def _declare(lib):
         "cv_attn_decode": [P, P, L, P, I, P, P, I, I, I, I, I, P],
         "cv_adamw_step": [P, P, P, P, P, L, F, F, F, F, F, I, P, F, P],
         "cv_sumsq_bf16": [P, L, P, P],
+        "cv_adamw_step_multi": [P, I, F, F, F, P, F, P],
+        "cv_sumsq_bf16_multi": [P, I, P, P],
         "cv_clip_coef": [P, F, P, P, P],
         "cv_conv2d_k4s2": [P, P, P, P, I, I, I, I, I, I, P],
         "cv_conv_transpose2d_k4s2": [P, P, P, P, I, I, I, I, I, I, P],

@@ -156,13 +156,14 @@ __global__ void __launch_bounds__(512)
 ln_bwd_fused_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const float* __restrict__ mean_in,
                     const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ gamma,
                     const float* __restrict__ dres, TDx* __restrict__ dx, float* __restrict__ partials, int rows,
-                    int cols, int rows_per_cta, const DropoutArgs drop) {
+                    int cols, int rows_per_cta, const DropoutArgs drop, int want_dxsum) {
     __shared__ float red[2][16][2 * FB_R];          // [buffer][warp][s1 x R, s2 x R]
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c0 = threadIdx.x * 4, c1 = c0 + cols / 2;
     const float4 g0 = ld4(gamma + c0), g1 = ld4(gamma + c1);
     float4 dg0 = make_float4(0.f, 0.f, 0.f, 0.f), dg1 = dg0, db0 = dg0, db1 = dg0;
+    float4 ds0 = dg0, ds1 = dg0;                     // column sums of dx (= bias gradient of the GEMM that produced x)
     const float inv_n = 1.0f / cols;
     const int r_begin = blockIdx.x * rows_per_cta;
     const int r_end = min(rows, r_begin + rows_per_cta);
@@ -228,12 +229,30 @@ ln_bwd_fused_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const
                 }
                 st4(dx + off + c0, o0);
                 st4(dx + off + c1, o1);
+                if (want_dxsum) {   // summed as stored (rounded to the output type), like a separate column-sum pass
+                    ds0.x += round_as(o0.x, dx); ds0.y += round_as(o0.y, dx); ds0.z += round_as(o0.z, dx); ds0.w += round_as(o0.w, dx);
+                    ds1.x += round_as(o1.x, dx); ds1.y += round_as(o1.y, dx); ds1.z += round_as(o1.z, dx); ds1.w += round_as(o1.w, dx);
+                }
             }
         }
     }
-    float* pout = partials + (size_t)blockIdx.x * 2 * cols;
+    const int nacc = want_dxsum ? 3 : 2;
+    float* pout = partials + (size_t)blockIdx.x * nacc * cols;
     st4(pout + c0, dg0); st4(pout + c1, dg1);
     st4(pout + cols + c0, db0); st4(pout + cols + c1, db1);
+    if (want_dxsum) { st4(pout + 2 * cols + c0, ds0); st4(pout + 2 * cols + c1, ds1); }
+}
+
+// reduces [nparts][nacc][cols] partials into up to three bf16 vectors
+__global__ void ln_bwd_finalize3_kernel(const float* __restrict__ partials, int nparts, int cols, int nacc,
+                                        __nv_bfloat16* __restrict__ o0, __nv_bfloat16* __restrict__ o1,
+                                        __nv_bfloat16* __restrict__ o2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nacc * cols) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * nacc * cols + i];
+    const int which = i / cols, c = i - which * cols;
+    (which == 0 ? o0 : (which == 1 ? o1 : o2))[c] = __float2bfloat16_rn(s);
 }
 
 // dgamma[c] = sum_r dy[r,c] * xhat[r,c], dbeta[c] = sum_r dy[r,c].  Thread per column (coalesced across columns),
@@ -314,14 +333,14 @@ extern "C" int cv_layernorm_absmax_fwd(const void* x, int x_is_bf16, const float
 extern "C" int64_t cv_layernorm_bwd_workspace_bytes(int rows, int cols) {
     (void)rows;
     const int64_t parts = 2 * cvh::num_sms() > PARAM_ROW_SPLITS ? 2 * cvh::num_sms() : PARAM_ROW_SPLITS;
-    return parts * 2 * cols * sizeof(float);
+    return parts * 3 * cols * sizeof(float);
 }
 
 extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16,
                                        const float* mean, const float* rstd, const void* gamma, const float* dres,
                                        void* dx, int dx_is_bf16, void* dgamma, void* dbeta, float* workspace,
                                        int rows, int cols, float dropout_p, uint64_t seed, uint32_t site,
-                                       void* stream) {
+                                       void* dxsum, void* stream) {
     const cvh::HostDropout hd = cvh::make_dropout(dropout_p, seed, site);
     DropoutArgs dargs;
     dargs.p = hd.p; dargs.scale = hd.scale; dargs.threshold = hd.threshold; dargs.stream = hd.stream; dargs.seed = hd.seed;
@@ -344,7 +363,7 @@ extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void*
 #define LAUNCH_F(TI, TDY, TDX)                                                                                 \
     ln_bwd_fused_kernel<TI, TDY, TDX><<<fgrid, threads, 0, s>>>(static_cast<const TI*>(x), static_cast<const TDY*>(dy), \
                                                                 mean, rstd, g, dres, static_cast<TDX*>(dx), workspace,   \
-                                                                rows, cols, rows_per_cta, dargs)
+                                                                rows, cols, rows_per_cta, dargs, dxsum != nullptr)
         if (x_is_bf16 && !dy_is_bf16 && dx_is_bf16) LAUNCH_F(__nv_bfloat16, float, __nv_bfloat16);
         else if (!x_is_bf16 && dy_is_bf16 && !dx_is_bf16) LAUNCH_F(float, __nv_bfloat16, float);
         else if (!x_is_bf16 && !dy_is_bf16 && !dx_is_bf16) LAUNCH_F(float, float, float);
@@ -352,13 +371,15 @@ extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void*
         else return cvh::fail_arg(__func__, "unsupported dtype combination");
 #undef LAUNCH_F
         CV_LAUNCH_CHECK();
-        const int n2 = 2 * cols;
-        ln_bwd_finalize_kernel<<<(n2 + 255) / 256, 256, 0, s>>>(workspace, fgrid, cols,
-                                                               static_cast<__nv_bfloat16*>(dgamma),
-                                                               static_cast<__nv_bfloat16*>(dbeta));
+        const int nacc = dxsum != nullptr ? 3 : 2;
+        ln_bwd_finalize3_kernel<<<(nacc * cols + 255) / 256, 256, 0, s>>>(workspace, fgrid, cols, nacc,
+                                                                         static_cast<__nv_bfloat16*>(dgamma),
+                                                                         static_cast<__nv_bfloat16*>(dbeta),
+                                                                         static_cast<__nv_bfloat16*>(dxsum));
         CV_LAUNCH_CHECK();
         return 0;
     }
+    CV_REQUIRE(dxsum == nullptr, "the column sum of dx is only produced by the fused path (hidden size % 256 == 0)");
     const int splits = rows < PARAM_ROW_SPLITS ? rows : PARAM_ROW_SPLITS;
     dim3 pgrid((cols + 127) / 128, splits);
 #define LAUNCH(TI, TDY, TDX)                                                                                   \

@@ -196,22 +196,25 @@ def layer_backward(d_out, saved, P, heads, b, sq, sep, drops=None):
     h = x.shape[1]
     M = b * sq
     # out = y + LN4(mlp_out)
-    d_mlp_out, dg4, db4 = ops.layernorm_absmax_bwd(mlp_out, d_out, mean4, rstd4, g4, dx_dtype=torch.bfloat16,
-                                                   dropout=drops['mlp'] if drops else None)
+    fuse_bias = h % 256 == 0          # the fused LN backward also returns the column sums of dx = the bias gradient
+    r4 = ops.layernorm_absmax_bwd(mlp_out, d_out, mean4, rstd4, g4, dx_dtype=torch.bfloat16,
+                                  dropout=drops['mlp'] if drops else None, want_dxsum=fuse_bias)
+    d_mlp_out, dg4, db4 = r4[:3]
     d_pre = ops.gemm(d_mlp_out, w2, b_mn_major=True, act=ops.ACT_GELU_GRAD, aux=pre)   # (dY W2) * gelu'(pre)
     dw2 = ops.gemm(d_mlp_out, h4, a_mn_major=True, b_mn_major=True)
-    dbb2 = ops.colsum(d_mlp_out)
+    dbb2 = r4[3] if fuse_bias else ops.colsum(d_mlp_out)
     d_ln2 = ops.gemm(d_pre, w1, b_mn_major=True)
     dw1 = ops.gemm(d_pre, ln2, a_mn_major=True, b_mn_major=True)
     dbb1 = ops.colsum(d_pre)
     d_y, dg2, db2 = ops.layernorm_absmax_bwd(y, d_ln2, mean2, rstd2, g2, dres=d_out, dx_dtype=torch.float32)
     # y = x + LN3(attn_out)
-    d_attn_out, dg3, db3 = ops.layernorm_absmax_bwd(attn_out, d_y, mean3, rstd3, g3, dx_dtype=torch.bfloat16,
-                                                    dropout=drops['out'] if drops else None)
+    r3 = ops.layernorm_absmax_bwd(attn_out, d_y, mean3, rstd3, g3, dx_dtype=torch.bfloat16,
+                                  dropout=drops['out'] if drops else None, want_dxsum=fuse_bias)
+    d_attn_out, dg3, db3 = r3[:3]
     ctx2 = ctx.view(M, h)
     d_ctx = ops.gemm(d_attn_out, wd, b_mn_major=True)
     dwd = ops.gemm(d_attn_out, ctx2, a_mn_major=True, b_mn_major=True)
-    dbd = ops.colsum(d_attn_out)
+    dbd = r3[3] if fuse_bias else ops.colsum(d_attn_out)
     qkv3 = qkv.view(b, sq, 3 * h)
     use_ad = bool(drops) and drops['attn'][0] > 0
     d_qkv = ops.attn_bwd(qkv3[..., :h], qkv3[..., h:2 * h], qkv3[..., 2 * h:], ctx, d_ctx.view(b, sq, h), lse, heads,

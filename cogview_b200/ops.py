@@ -109,8 +109,9 @@ def dropout_mask(n, p, seed, site, device="cuda"):
     return out
 
 
-def layernorm_absmax_bwd(x, dy, mean, rstd, gamma, *, dres=None, dx_dtype=torch.float32, dropout=None):
-    """Returns (dx, dgamma, dbeta)."""
+def layernorm_absmax_bwd(x, dy, mean, rstd, gamma, *, dres=None, dx_dtype=torch.float32, dropout=None,
+                         want_dxsum=False):
+    """Returns (dx, dgamma, dbeta) [+ column sums of dx when want_dxsum (hidden size % 256 == 0)]."""
     require_cuda(x, dy, mean, rstd, gamma, dres)
     assert x.is_contiguous() and dy.is_contiguous()
     rows, cols = x.shape
@@ -118,13 +119,16 @@ def layernorm_absmax_bwd(x, dy, mean, rstd, gamma, *, dres=None, dx_dtype=torch.
     dgamma = torch.empty(cols, dtype=torch.bfloat16, device=x.device)
     dbeta = torch.empty(cols, dtype=torch.bfloat16, device=x.device)
     ws = torch.empty(lib().cv_layernorm_bwd_workspace_bytes(rows, cols) // 4, dtype=torch.float32, device=x.device)
+    dxsum = torch.empty(cols, dtype=torch.bfloat16, device=x.device) if want_dxsum else None
     if dres is not None:
         assert dres.dtype == torch.float32 and dres.is_contiguous()
     rc = lib().cv_layernorm_absmax_bwd(ptr(x), int(x.dtype == torch.bfloat16), ptr(dy),
                                        int(dy.dtype == torch.bfloat16), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres),
                                        ptr(dx), int(dx_dtype == torch.bfloat16), ptr(dgamma), ptr(dbeta), ptr(ws),
-                                       rows, cols, *_drop3(dropout), stream_ptr())
+                                       rows, cols, *_drop3(dropout), ptr(dxsum), stream_ptr())
     check(rc, "cv_layernorm_absmax_bwd")
+    if want_dxsum:
+        return dx, dgamma, dbeta, dxsum
     return dx, dgamma, dbeta
 
 

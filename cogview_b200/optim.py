@@ -3,8 +3,10 @@ FP16_Optimizer + apex FusedAdam + mpu.clip_grad_norm sequence (pretrain_gpt2.py:
 fp16/fp16.py:291-310, :399-453; mpu/grads.py:28-74).  bf16 needs no loss scaling, so the dynamic loss scaler
 disappears; the NaN/inf guard of train_step (pretrain_gpt2.py:415-417) stays with the caller.
 
-The clip coefficient is computed on the device (cv_sumsq_bf16 + cv_clip_coef) and consumed by cv_adamw_step
-through a device pointer, so a step never synchronises with the host."""
+The clip coefficient is computed on the device (cv_sumsq_bf16_multi + cv_clip_coef) and consumed by
+cv_adamw_step_multi through a device pointer, so a step never synchronises with the host.  The whole parameter
+list is one table (cv_adamw_entry, include/cogview_b200.h) -> three launches per step instead of two per tensor."""
+import numpy as np
 import torch
 
 from ._lib import check, lib, ptr, stream_ptr
@@ -16,7 +18,31 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.max_grad_norm = float(max_grad_norm)
         self._scal = None
+        self._tables = None          # (pinned host staging x2, device table), rebuilt when the parameter list changes
+        self._flip = 0
         self.last_grad_norm = None   # device tensor (1,) after step() when clipping is on
+
+    _ENTRY = np.dtype([('param', '<u8'), ('grad', '<u8'), ('master', '<u8'), ('m', '<u8'), ('v', '<u8'), ('n', '<i8'),
+                       ('lr', '<f4'), ('wd', '<f4'), ('bc1', '<f4'), ('bc2', '<f4')])   # = cv_adamw_entry, 64 bytes
+
+    def _table(self, plist, dev):
+        """Fills the device-resident cv_adamw_entry table for this step (gradient pointers may move between steps)."""
+        n = len(plist)
+        if self._tables is None or self._tables[2].numel() != n * 64 or self._tables[2].device != dev:
+            host = [torch.empty(n * 64, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._tables = (host[0], host[1], torch.empty(n * 64, dtype=torch.uint8, device=dev))
+        self._flip ^= 1                                   # double-buffered: the previous step's copy may be in flight
+        host = self._tables[self._flip]
+        rec = host.numpy().view(self._ENTRY)
+        for i, (group, p) in enumerate(plist):
+            st = self._state_for(p)
+            st['step'] += 1
+            b1, b2 = group['betas']
+            rec[i] = (p.data_ptr(), p.grad.data_ptr(), st['master'].data_ptr(), st['exp_avg'].data_ptr(),
+                      st['exp_avg_sq'].data_ptr(), p.numel(), group['lr'], group['weight_decay'],
+                      1.0 - b1 ** st['step'], 1.0 - b2 ** st['step'])
+        self._tables[2].copy_(host, non_blocking=True)
+        return self._tables[2]
 
     def _state_for(self, p):
         st = self.state[p]
@@ -36,26 +62,24 @@ class FusedAdamW(torch.optim.Optimizer):
         if not plist:
             return None
         dev = plist[0][1].device
+        for group, p in plist:
+            assert p.dtype == torch.bfloat16 and p.is_contiguous(), "FusedAdamW expects contiguous bf16 parameters"
+            g = p.grad
+            assert g.dtype == torch.bfloat16 and g.is_contiguous(), "FusedAdamW expects contiguous bf16 gradients"
+        assert len({(g['betas'], g['eps']) for g, _ in plist}) == 1, "betas / eps must be the same for all groups"
+        b1, b2 = plist[0][0]['betas']
+        eps = plist[0][0]['eps']
+        table = self._table(plist, dev)
         coef = None
         if self.max_grad_norm > 0:
             if self._scal is None or self._scal.device != dev:
                 self._scal = torch.zeros(3, dtype=torch.float32, device=dev)
             self._scal.zero_()
-            for _, p in plist:
-                g = p.grad
-                assert g.dtype == torch.bfloat16 and g.is_contiguous(), "FusedAdamW expects contiguous bf16 gradients"
-                check(L.cv_sumsq_bf16(ptr(g), g.numel(), ptr(self._scal[0:1]), stream), "cv_sumsq_bf16")
+            check(L.cv_sumsq_bf16_multi(ptr(table), len(plist), ptr(self._scal[0:1]), stream), "cv_sumsq_bf16_multi")
             check(L.cv_clip_coef(ptr(self._scal[0:1]), self.max_grad_norm, ptr(self._scal[1:2]), ptr(self._scal[2:3]),
                                  stream), "cv_clip_coef")
             coef = self._scal[1:2]
             self.last_grad_norm = self._scal[2:3]
-        for group, p in plist:
-            assert p.dtype == torch.bfloat16 and p.is_contiguous(), "FusedAdamW expects contiguous bf16 parameters"
-            st = self._state_for(p)
-            st['step'] += 1
-            b1, b2 = group['betas']
-            check(L.cv_adamw_step(ptr(p), ptr(p.grad), ptr(st['master']), ptr(st['exp_avg']), ptr(st['exp_avg_sq']),
-                                  p.numel(), float(group['lr']), float(b1), float(b2), float(group['eps']),
-                                  float(group['weight_decay']), int(st['step']), ptr(coef), 1.0, stream),
-                  "cv_adamw_step")
+        check(L.cv_adamw_step_multi(ptr(table), len(plist), float(b1), float(b2), float(eps), ptr(coef), 1.0, stream),
+              "cv_adamw_step_multi")
         return None

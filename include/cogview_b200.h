@@ -69,11 +69,12 @@ int cv_layernorm_absmax_fwd(const void* x, int x_is_bf16, const float* absmax_in
 int64_t cv_layernorm_bwd_workspace_bytes(int rows, int cols);
 /* dx = LN'(dy) (+ dres); dgamma/dbeta bf16 [cols]; workspace of cv_layernorm_bwd_workspace_bytes() bytes.
  * The abs-max scale is a detached constant in the reference (x.abs().max().detach()), and so it is here. */
-/* dropout_p > 0: x was the output of dropout site (seed, site) — dx is multiplied by that site's keep mask / (1-p). */
+/* dropout_p > 0: x was the output of dropout site (seed, site) — dx is multiplied by that site's keep mask / (1-p).
+ * dxsum (bf16 [cols], may be NULL): column sums of dx — the bias gradient of the linear layer that produced x. */
 int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, const float* mean,
                             const float* rstd, const void* gamma, const float* dres, void* dx, int dx_is_bf16,
                             void* dgamma, void* dbeta, float* workspace, int rows, int cols, float dropout_p,
-                            uint64_t seed, uint32_t site, void* stream);
+                            uint64_t seed, uint32_t site, void* dxsum, void* stream);
 int cv_absmax(const void* x, int x_is_bf16, int64_t n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -171,6 +172,20 @@ int cv_adamw_step(void* param, const void* grad, float* master, float* m, float*
                   float beta2, float eps, float weight_decay, int step, const float* grad_scale_dev,
                   float grad_scale, void* stream);
 int cv_sumsq_bf16(const void* x, int64_t n, float* out, void* stream);   /* *out += sum(x^2) */
+/* Multi-tensor forms: one launch over a device-resident table (the whole parameter list of a model).
+ * Pointers must be aligned as for cv_adamw_step / cv_sumsq_bf16; bias_correction{1,2} = 1 - beta{1,2}^step. */
+typedef struct cv_adamw_entry {
+    void* param;          /* bf16 [n] */
+    const void* grad;     /* bf16 [n] */
+    float* master;        /* fp32 [n] */
+    float* m;             /* fp32 [n] */
+    float* v;             /* fp32 [n] */
+    int64_t n;
+    float lr, weight_decay, bias_correction1, bias_correction2;
+} cv_adamw_entry;         /* 64 bytes */
+int cv_adamw_step_multi(const cv_adamw_entry* table_dev, int count, float beta1, float beta2, float eps,
+                        const float* grad_scale_dev, float grad_scale, void* stream);
+int cv_sumsq_bf16_multi(const cv_adamw_entry* table_dev, int count, float* out, void* stream); /* over .grad/.n */
 int cv_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -90,6 +90,11 @@ def test_layernorm_absmax_fwd_bwd(ops, rows, cols):
     y2_ref.backward(dy2)
     dx2, _, _ = ops.layernorm_absmax_bwd(xb.cuda(), dy2.cuda(), mean2, rstd2, gamma.cuda(), dx_dtype=torch.bfloat16)
     assert rel_err(dx2, xr2.grad) < 1e-2
+    # (3) the fused kernel's extra output: column sums of dx (bias gradient of the producing linear layer)
+    dx3, dg3, db3, dxsum = ops.layernorm_absmax_bwd(xb.cuda(), dy2.cuda(), mean2, rstd2, gamma.cuda(),
+                                                    dx_dtype=torch.bfloat16, want_dxsum=True)
+    assert torch.equal(dx3, dx2)
+    assert rel_err(dxsum, dx2.float().sum(0)) < 1e-2
 
 
 @pytest.mark.parametrize("b,heads,sq,sk,sep", [(2, 4, 128, 128, 0), (2, 3, 200, 200, 0), (1, 2, 1088, 1088, 0),
@@ -184,24 +189,31 @@ def test_attention_bwd_matches_autograd_of_standard_attention(ops, b, heads, s, 
 
 
 def test_fused_adamw_matches_torch_adamw_on_fp32_masters(ops):
+    """Multi-tensor AdamW + global-norm clipping over two parameter groups (weight decay / no weight decay,
+    gpt2_get_params_for_weight_decay_optimization) against torch.optim.AdamW on fp32 copies."""
     from cogview_b200.optim import FusedAdamW
     g = torch.Generator().manual_seed(11)
-    w0 = torch.randn((300, 257), generator=g)
-    p = torch.nn.Parameter(bf(w0).cuda())
-    ref = torch.nn.Parameter(bf(w0).float())
-    opt = FusedAdamW([{'params': [p], 'weight_decay': 0.01}], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, max_grad_norm=1.0)
-    ropt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.01)
+    shapes = [(300, 257), (2560,), (7,), (1024, 64)]
+    w0 = [torch.randn(sh, generator=g) for sh in shapes]
+    ps = [torch.nn.Parameter(bf(w).cuda()) for w in w0]
+    refs = [torch.nn.Parameter(bf(w).float()) for w in w0]
+    opt = FusedAdamW([{'params': [ps[0], ps[3]], 'weight_decay': 0.01}, {'params': [ps[1], ps[2]], 'weight_decay': 0.0}],
+                     lr=1e-2, betas=(0.9, 0.95), eps=1e-8, max_grad_norm=1.0)
+    ropt = torch.optim.AdamW([{'params': [refs[0], refs[3]], 'weight_decay': 0.01},
+                              {'params': [refs[1], refs[2]], 'weight_decay': 0.0}], lr=1e-2, betas=(0.9, 0.95), eps=1e-8)
     for it in range(3):
-        gr = bf(torch.randn((300, 257), generator=g))
-        p.grad = gr.cuda()
-        ref.grad = gr.float().clone()
-        gn = torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        for p, r, sh in zip(ps, refs, shapes):
+            gr = bf(torch.randn(sh, generator=g))
+            p.grad = gr.cuda()
+            r.grad = gr.float().clone()
+        gn = torch.nn.utils.clip_grad_norm_(refs, 1.0)
         opt.step()
         ropt.step()
         assert abs(opt.last_grad_norm.item() - gn.item()) < 1e-3 * gn.item()
-    master = opt.state[p]['master'].cpu()
-    assert (master - ref.detach()).abs().max().item() < 1e-5
-    assert torch.equal(p.detach().cpu(), bf(master))
+    for p, r in zip(ps, refs):
+        master = opt.state[p]['master'].cpu()
+        assert (master - r.detach()).abs().max().item() < 1e-5
+        assert torch.equal(p.detach().cpu(), bf(master))
 
 
 @pytest.mark.parametrize("M,N,K,act", [(4, 7680, 2560, 0), (4, 2560, 10240, 0), (2, 1024, 256, 1), (1, 58240, 256, 0),
