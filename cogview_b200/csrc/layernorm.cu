@@ -243,16 +243,33 @@ ln_bwd_fused_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, const
     if (want_dxsum) { st4(pout + 2 * cols + c0, ds0); st4(pout + 2 * cols + c1, ds1); }
 }
 
-// reduces [nparts][nacc][cols] partials into up to three bf16 vectors
-__global__ void ln_bwd_finalize3_kernel(const float* __restrict__ partials, int nparts, int cols, int nacc,
-                                        __nv_bfloat16* __restrict__ o0, __nv_bfloat16* __restrict__ o1,
-                                        __nv_bfloat16* __restrict__ o2) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nacc * cols) return;
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * nacc * cols + i];
-    const int which = i / cols, c = i - which * cols;
-    (which == 0 ? o0 : (which == 1 ? o1 : o2))[c] = __float2bfloat16_rn(s);
+// reduces [nparts][nacc][cols] partials into up to three bf16 vectors; block = 32 columns x 8 part groups
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize3_kernel(const float* __restrict__ partials, int nparts, int cols, int nacc,
+                        __nv_bfloat16* __restrict__ o0, __nv_bfloat16* __restrict__ o1,
+                        __nv_bfloat16* __restrict__ o2) {
+    __shared__ float sh[8][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;                    // index into [nacc][cols]
+    float s0 = 0.f, s1 = 0.f;
+    if (i < nacc * cols) {
+        const size_t stride = (size_t)nacc * cols;
+        int p = grp;
+        for (; p + 8 < nparts; p += 16) {
+            s0 += partials[(size_t)p * stride + i];
+            s1 += partials[(size_t)(p + 8) * stride + i];
+        }
+        if (p < nparts) s0 += partials[(size_t)p * stride + i];
+    }
+    sh[grp][lane] = s0 + s1;
+    __syncthreads();
+    if (grp == 0 && i < nacc * cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += sh[g][lane];
+        const int which = i / cols, c = i - which * cols;
+        (which == 0 ? o0 : (which == 1 ? o1 : o2))[c] = __float2bfloat16_rn(s);
+    }
 }
 
 // dgamma[c] = sum_r dy[r,c] * xhat[r,c], dbeta[c] = sum_r dy[r,c].  Thread per column (coalesced across columns),
@@ -372,7 +389,7 @@ extern "C" int cv_layernorm_absmax_bwd(const void* x, int x_is_bf16, const void*
 #undef LAUNCH_F
         CV_LAUNCH_CHECK();
         const int nacc = dxsum != nullptr ? 3 : 2;
-        ln_bwd_finalize3_kernel<<<(nacc * cols + 255) / 256, 256, 0, s>>>(workspace, fgrid, cols, nacc,
+        ln_bwd_finalize3_kernel<<<(nacc * cols + 31) / 32, 256, 0, s>>>(workspace, fgrid, cols, nacc,
                                                                          static_cast<__nv_bfloat16*>(dgamma),
                                                                          static_cast<__nv_bfloat16*>(dbeta),
                                                                          static_cast<__nv_bfloat16*>(dxsum));

@@ -12,13 +12,14 @@ import bench
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "train"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    dropout = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
     cfg = bench.MODEL_4B
     torch.cuda.set_device(0)
     if what == "train":
         from cogview_b200 import mpu
         from cogview_b200.model import gpt2_get_params_for_weight_decay_optimization
         from cogview_b200.optim import FusedAdamW
-        model = bench.build_model(cfg, 0, "cuda").train()
+        model = bench.build_model(cfg, 0, "cuda", dropout=dropout).train()
         groups = gpt2_get_params_for_weight_decay_optimization(model)
         opt = FusedAdamW(groups, lr=4e-4, weight_decay=0.01, max_grad_norm=1.0)
         b, s = 4, 1088
