@@ -29,7 +29,7 @@ constexpr int TILE_BYTES = BLK * HD * 2;      // 16 KB: one [128 x 64] bf16 tile
 constexpr int PT_BYTES = BLK * BLK * 2;       // 32 KB: [128 keys x 128 queries] bf16
 constexpr int QDO_STAGES = 2;
 constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + QDO_STAGES * 2 * TILE_BYTES /*Q,dO*/ + 2 * PT_BYTES /*P^T,dS^T*/ +
-                           QDO_STAGES * 2 * BLK * 4 /*lse2, D*/ + QDO_STAGES * BLK * 16 /*keep bits*/ + 1024 + 256;
+                           QDO_STAGES * 2 * BLK * 4 /*lse2, D*/ + 1024 + 256;
 constexpr int NUM_THREADS = 192;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -41,7 +41,8 @@ struct BwdParams {
     const float* delta;  // [b, heads, s]
     float* dq_acc;       // [b, s, heads*HD] fp32, zero-initialised
     __nv_bfloat16* dqkv; // [b, s, 3*heads*HD]
-    const uint32_t* drop_mask;  // keep bits written by the forward ([b, heads, s, nkb, 4]) or null (no dropout)
+    const uint32_t* drop_mask;  // keep bits written by the forward, key-major ([b, heads, nkb*128, nqb, 4]: the 128 query
+                                // bits of (key, query block) are one 16-byte load for the thread that owns the key) or null
     float drop_scale;           // 1 / (1 - p)
 };
 
@@ -62,8 +63,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* sDST = sPT + PT_BYTES;
     float* sLse = reinterpret_cast<float*>(sDST + PT_BYTES);       // [stages][128]
     float* sDelta = sLse + QDO_STAGES * BLK;
-    uint4* sKeep = reinterpret_cast<uint4*>(sDelta + QDO_STAGES * BLK);   // [stages][128 queries] 128 keep bits each
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sKeep + QDO_STAGES * BLK);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + QDO_STAGES * BLK);
     uint64_t* kv_full = bars;                  // 1
     uint64_t* qdo_full = bars + 1;             // [2]
     uint64_t* qdo_empty = qdo_full + QDO_STAGES;
@@ -178,6 +178,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
         const float masked_val = -10000.0f * LOG2E;
         const size_t stat_base = ((size_t)batch * p.heads + head) * p.s;
+        const size_t keep_base = ((size_t)batch * p.heads + head) * (size_t)nqb * BLK;   // key rows are padded to blocks
         int stage = 0;
         float pre_lse, pre_delta;
         uint4 pre_keep = make_uint4(0, 0, 0, 0);
@@ -185,8 +186,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int qn = i_start * BLK + epi_tid;
             pre_lse = (qn < p.s) ? p.lse[stat_base + qn] * LOG2E : 0.f;
             pre_delta = (qn < p.s) ? p.delta[stat_base + qn] : 0.f;
-            if (p.drop_mask != nullptr && qn < p.s)
-                pre_keep = *reinterpret_cast<const uint4*>(p.drop_mask + ((stat_base + qn) * (size_t)nqb + kb) * 4);
+            if (p.drop_mask != nullptr)
+                pre_keep = *reinterpret_cast<const uint4*>(p.drop_mask + ((keep_base + kj) * (size_t)nqb + i_start) * 4);
         }
         for (int t = 0; t < ntiles; ++t) {
             const int q0 = (i_start + t) * BLK;
@@ -194,14 +195,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // publish them, then start the fetch for the next tile so its global-load latency is off the critical path
             sLse[stage * BLK + epi_tid] = pre_lse;
             sDelta[stage * BLK + epi_tid] = pre_delta;
-            if (p.drop_mask != nullptr) sKeep[stage * BLK + epi_tid] = pre_keep;
+            const uint4 kw = pre_keep;                  // this key's keep bits over the 128 queries of the tile
             if (t + 1 < ntiles) {
                 const int qn = q0 + BLK + epi_tid;
                 pre_lse = (qn < p.s) ? p.lse[stat_base + qn] * LOG2E : 0.f;
                 pre_delta = (qn < p.s) ? p.delta[stat_base + qn] : 0.f;
                 if (p.drop_mask != nullptr)
-                    pre_keep = (qn < p.s) ? *reinterpret_cast<const uint4*>(p.drop_mask + ((stat_base + qn) * (size_t)nqb + kb) * 4)
-                                          : make_uint4(0, 0, 0, 0);
+                    pre_keep = *reinterpret_cast<const uint4*>(p.drop_mask +
+                                                               ((keep_base + kj) * (size_t)nqb + i_start + t + 1) * 4);
             }
             named_bar_sync(1, 128);
             mbar_wait(sdp_full, t & 1);
@@ -211,7 +212,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                   ((k0 + BLK <= p.sep_eff) || (k0 + BLK - 1 <= q0));
             const float* lse2 = sLse + stage * BLK;
             const float* dlt = sDelta + stage * BLK;
-            const uint32_t* keepw = reinterpret_cast<const uint32_t*>(sKeep + stage * BLK) + q;   // word row/32 == q
             const bool use_drop = p.drop_mask != nullptr;
             uint8_t* prow = sPT + row * 128;
             uint8_t* drow = sDST + row * 128;
@@ -222,7 +222,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tmem_ld_x32(lane_addr + TM_DPT + c * 32, dr);
                 tmem_ld_wait();
                 float pv[32], dv[32];
-                if (full_vis && !use_drop) {           // interior tile, no dropout: branch-free inner loop
+                const uint32_t kwc = c == 0 ? kw.x : (c == 1 ? kw.y : (c == 2 ? kw.z : kw.w));
+                if (full_vis && use_drop) {            // interior tile with dropout: branch-free, bit i of kwc = query col
+                    const float ds = p.drop_scale;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c * 32 + i;
+                        const bool keep = (kwc >> i) & 1u;
+                        const float pr = exp2f(__uint_as_float(sr[i]) * p.scale_log2 - lse2[col]);
+                        // dP flows back through the keep mask; dV sees the dropped probabilities
+                        const float dp = keep ? __uint_as_float(dr[i]) * ds : 0.f;
+                        pv[i] = keep ? pr * ds : 0.f;
+                        dv[i] = pr * (dp - dlt[col]) * p.scale;
+                    }
+                } else if (full_vis) {                 // interior tile, no dropout: branch-free inner loop
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int col = c * 32 + i;
@@ -247,7 +260,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         float dp = __uint_as_float(dr[i]);
                         float pdrop = pr;
                         if (use_drop) {   // dP flows back through the keep mask; dV sees the dropped probabilities
-                            const bool keep = (keepw[col * 4] >> lane) & 1u;
+                            const bool keep = (kwc >> i) & 1u;
                             dp = keep ? dp * p.drop_scale : 0.f;
                             pdrop = keep ? pr * p.drop_scale : 0.f;
                         }

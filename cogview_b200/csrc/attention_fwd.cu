@@ -47,8 +47,12 @@ struct AttnParams {
     int64_t bso;        // batch stride of out (elements)
     float* lse;         // [b, heads, sq] natural-log LSE, or null
     DropoutArgs drop;   // attention-probability dropout (mpu/sparse_transformer.py:667-669); p = 0 disables
-    uint32_t* drop_mask;// [b, heads, sq, nkb_all, 4]: keep bits of each (query, 128-key tile), saved for the backward
+    uint32_t* drop_mask;// two regions of b*heads*nkb_all*nqb_all*128 uint4 each, written by attn_dropout_mask_kernel:
+                        //  [0] key-major [b, heads, nkb_all*128 (key), nqb_all, 4]: word w of (key, query block) holds
+                        //      queries qb*128 + 32w .. +31 (what the backward consumes: one 16-byte load per key row)
+                        //  [1] query-major [b, heads, nqb_all*128 (query), nkb_all, 4]: what this kernel consumes
     int nkb_all;        // ceil(sk / 128)
+    int nqb_all;        // ceil(sq / 128)
 };
 
 template <bool DROPOUT>
@@ -165,8 +169,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < HD; ++i) o[i] = 0.f;
         const float masked_val = -10000.0f * LOG2E;
+        const uint4* keep_row = nullptr;
+        uint4 pre_keep = make_uint4(0u, 0u, 0u, 0u);
+        if (DROPOUT) {
+            const size_t region = (size_t)p.b * p.heads * p.nkb_all * p.nqb_all * (BQ * 4);   // words per region
+            keep_row = reinterpret_cast<const uint4*>(p.drop_mask + region) +
+                       (((size_t)batch * p.heads + head) * p.nqb_all * BQ + qi) * p.nkb_all;
+            pre_keep = keep_row[0];
+        }
 
         for (int j = 0; j < nkb; ++j) {
+            uint4 kw = make_uint4(0u, 0u, 0u, 0u);      // keep bits of this row over the tile's 128 keys
+            if (DROPOUT) {
+                kw = pre_keep;
+                if (j + 1 < nkb) pre_keep = keep_row[j + 1];
+            }
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
             const int k0 = j * BKV;
@@ -197,7 +214,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float alpha = exp2f(m - mx);          // m = -inf on the first tile -> 0
             m = mx;
             float psum = 0.f;
-            uint32_t keep_bits[4] = {0u, 0u, 0u, 0u};
             uint8_t* prow = sP + (j & 1) * P_BYTES + row * 128;
 #pragma unroll
             for (int c = 0; c < BKV / 8; ++c) {         // 16 chunks of 8 keys (16 bytes)
@@ -211,21 +227,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pk);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) psum += __low2float(pb[t]) + __high2float(pb[t]);
-                if (DROPOUT) {   // dropout acts on the normalised probabilities: the row sum stays undropped
-                    // one Philox call per 8 keys: eight 16-bit uniforms against a 16-bit threshold (p to within 2^-16)
-                    const uint64_t ctr = ((((uint64_t)batch * p.heads + head) * p.sq + qi) * p.nkb_all + j) * 16 + c;
-                    const uint4 r0 = philox4x32_10(p.drop.seed, ctr, p.drop.stream);
-                    const uint32_t thr16 = p.drop.threshold >> 16;
-                    const uint32_t rr[8] = {r0.x & 0xffffu, r0.x >> 16, r0.y & 0xffffu, r0.y >> 16,
-                                            r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
-                    uint32_t bits = 0;
+                if (DROPOUT) {   // dropout acts on the normalised probabilities: the row sum stays undropped; the
+                                 // 1/(1-p) scale is applied once to the output row at the end
+                    const uint32_t w = (c >> 2) == 0 ? kw.x : ((c >> 2) == 1 ? kw.y : ((c >> 2) == 2 ? kw.z : kw.w));
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const bool keep = rr[t] >= thr16;
-                        bits |= (keep ? 1u : 0u) << t;
-                        e[t] = keep ? e[t] * p.drop.scale : 0.f;
-                    }
-                    keep_bits[c >> 2] |= bits << ((c & 3) * 8);
+                    for (int t = 0; t < 8; ++t) e[t] = ((w >> ((c & 3) * 8 + t)) & 1u) ? e[t] : 0.f;
                     pk.x = pack_bf16x2(e[0], e[1]); pk.y = pack_bf16x2(e[2], e[3]);
                     pk.z = pack_bf16x2(e[4], e[5]); pk.w = pack_bf16x2(e[6], e[7]);
                 }
@@ -233,9 +239,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 *reinterpret_cast<uint4*>(prow + sub * (BQ * 128) + ((cc ^ (row & 7)) << 4)) = pk;
             }
             l = l * alpha + psum;
-            if (DROPOUT && qi < p.sq)
-                *reinterpret_cast<uint4*>(p.drop_mask + ((((size_t)batch * p.heads + head) * p.sq + qi) * p.nkb_all + j) * 4) =
-                    make_uint4(keep_bits[0], keep_bits[1], keep_bits[2], keep_bits[3]);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);
@@ -271,7 +274,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int i = 0; i < HD; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(r[i]);
         }
         if (qi < p.sq) {
-            const float inv_l = 1.0f / l;
+            const float inv_l = (DROPOUT ? p.drop.scale : 1.0f) / l;
             __nv_bfloat16* orow = p.out + (size_t)batch * p.bso + (size_t)qi * p.ldo + head * HD;
 #pragma unroll
             for (int c = 0; c < HD / 8; ++c) {
@@ -293,6 +296,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
+}
+
+// Keep decisions of the attention-probability dropout for every (query, key) pair of the visible tiles, generated
+// ahead of the attention kernel at full occupancy (inside the attention kernel the same work sits on the softmax
+// warps' critical path: measured +200 us per call at the 4B shape).  One thread per (query row, key tile): a
+// Philox4x32-10 call seeds four 32-step LCG streams, keep iff state >= p * 2^32.  Writes both layouts (AttnParams).
+__global__ void __launch_bounds__(128, 4)
+attn_dropout_mask_kernel(const AttnParams p) {
+    const int qb = blockIdx.x, j = blockIdx.y;
+    const int head = blockIdx.z % p.heads, batch = blockIdx.z / p.heads;
+    const int q0 = qb * BQ;
+    int kmax = q0 + BQ + p.off;
+    if (kmax < p.sep_eff) kmax = p.sep_eff;
+    if (kmax > p.sk) kmax = p.sk;
+    if (j * BKV >= kmax) return;                 // tile never visited by the attention kernels
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int qi = q0 + threadIdx.x;
+    const uint64_t ctr = (((uint64_t)batch * p.heads + head) * p.sq + qi) * p.nkb_all + j;
+    const uint4 r0 = philox4x32_10(p.drop.seed, ctr, p.drop.stream);
+    uint32_t rng[4] = {r0.x, r0.y, r0.z, r0.w};
+    uint32_t wrow[4], wkey[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t bits = 0u, mine = 0u;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            rng[g] = rng[g] * 1664525u + 1013904223u;
+            const bool keep = rng[g] >= p.drop.threshold;
+            bits |= (keep ? 1u : 0u) << t;
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);   // key 32g + t over this warp's 32 queries
+            if (lane == t) mine = bal;
+        }
+        wrow[g] = bits;
+        wkey[g] = mine;
+    }
+    const size_t bh = (size_t)batch * p.heads + head;
+    const size_t region = (size_t)p.b * p.heads * p.nkb_all * p.nqb_all * (BQ * 4);
+    reinterpret_cast<uint4*>(p.drop_mask + region)[(bh * p.nqb_all * BQ + qi) * p.nkb_all + j] =
+        make_uint4(wrow[0], wrow[1], wrow[2], wrow[3]);
+    uint32_t* dm = p.drop_mask + ((bh * p.nkb_all * BKV + j * BKV + lane) * p.nqb_all + qb) * 4 + wq;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) dm[(size_t)g * 32 * p.nqb_all * 4] = wkey[g];
 }
 
 // [b, s, cols] bf16 view: row stride ld, batch stride bs (elements); box [64 cols x box_rows rows x 1]
@@ -340,6 +385,7 @@ extern "C" int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* 
         p.drop.seed = hd.seed;
         p.drop_mask = drop_mask;
         p.nkb_all = (sk + BKV - 1) / BKV;
+        p.nqb_all = (sq + BQ - 1) / BQ;
     }
     static bool attr_set = false;
     if (!attr_set) {
@@ -348,7 +394,11 @@ extern "C" int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* 
         attr_set = true;
     }
     dim3 grid((sq + BQ - 1) / BQ, heads, b);
-    if (dropout_p > 0.f) attn_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
+    if (dropout_p > 0.f) {
+        attn_dropout_mask_kernel<<<dim3(p.nqb_all, p.nkb_all, b * heads), 128, 0, s>>>(p);
+        CV_LAUNCH_CHECK();
+        attn_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
+    }
     else attn_fwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
     CV_LAUNCH_CHECK();
     return 0;

@@ -148,7 +148,10 @@ def attn_fwd(q, k, v, heads, *, sep=0, want_lse=False, dropout=None):
     dp, dseed, dsite = _drop3(dropout)
     mask = None
     if dp > 0:
-        mask = torch.empty((b, heads, sq, (sk + 127) // 128, 4), dtype=torch.int32, device=q.device)
+        # keep bits in two layouts: [0] key-major [b, heads, key (padded to 128), query block, 4 x 32 queries] for the
+        # backward, [1] query-major [b, heads, query (padded), key block, 4 x 32 keys] for the forward kernel
+        mask = torch.empty((2, b, heads, ((sk + 127) // 128) * ((sq + 127) // 128) * 128, 4), dtype=torch.int32,
+                           device=q.device)
     rc = lib().cv_attn_fwd(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
                            v.stride(0), ptr(out), out.stride(1), out.stride(0), ptr(lse), b, heads, 64, sq, sk,
                            int(sep), dp, dseed, dsite, ptr(mask), stream_ptr())

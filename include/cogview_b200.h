@@ -88,8 +88,10 @@ int cv_absmax(const void* x, int x_is_bf16, int64_t n, float* out, void* stream)
  *          mpu/sparse_transformer.py:477-489)
  *   out: [b, sq, heads*64] bf16 (token-major, what the out-projection GEMM reads); lse: NULL or [b, heads, sq]
  *   dropout_p > 0: dropout on the attention probabilities (torch.nn.Dropout under the RNG-tracker fork,
- *         mpu/sparse_transformer.py:667-669) from the counter-based generator (seed, site); drop_mask
- *         [b, heads, sq, ceil(sk/128), 4] uint32 receives the keep bits for the backward.
+ *         mpu/sparse_transformer.py:667-669): one Philox4x32-10 call per (query, 128-key tile) of the counter-based
+ *         generator (seed, site) seeds four 32-step LCG streams, keep iff state >= p * 2^32.  drop_mask
+ *         [b, heads, ceil(sk/128)*128, ceil(sq/128), 4] uint32 receives the keep bits for the backward, key-major:
+ *         bit i of word w of (key, query block qb) is query qb*128 + 32w + i.
  * ---------------------------------------------------------------------------------------------- */
 int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
                 int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, float* lse, int b, int heads,
