@@ -12,6 +12,8 @@
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM;
 //               two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps tile i+1
 //   warps 2-5   epilogue: tcgen05.ld -> bias/GELU/abs-max -> each thread stores its row's 128 B straight to global
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/cogview_b200.h"
@@ -36,6 +38,8 @@ struct Cfg {
 struct GemmParams {
     int M, N, K;
     int num_m_blocks, num_n_blocks, num_k_blocks;
+    int split_from;             // tiles [0, split_from) are BN wide; each later BN-wide tile is walked as two BN/2 halves
+    int num_tiles;              // split_from + 2 * (number of split tiles)
     const __nv_bfloat16* bias;  // [N] or null
     int act;                    // 0 none, 1 tanh-GELU, 2 ReLU, 3 multiply by gelu'(aux) (GELU backward fused in dgrad)
     const __nv_bfloat16* aux;   // act == 3: pre-activation values [M, N] (leading dimension ldc)
@@ -46,6 +50,27 @@ struct GemmParams {
     __nv_bfloat16* c2;          // optional pre-activation output (bf16, same ldc)
     int64_t ldc;
 };
+
+// Tail-wave splitting: with T tiles on G persistent CTAs the last T % G tiles would occupy a whole wave while most
+// SMs idle (34 x 10 = 340 tiles of a 4352 x 2560 output on 148 SMs: 2.3 waves cost 3).  When those r tiles fit twice
+// (2r <= G) they are issued as 2r half-width tiles instead, so the last wave costs one half tile (~0.75 of a full one).
+struct TileCoord { int m0, n0, width; };
+template <int BN>
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile) {
+    TileCoord t;
+    if (tile < p.split_from) {
+        t.m0 = (tile % p.num_m_blocks) * BM;
+        t.n0 = (tile / p.num_m_blocks) * BN;
+        t.width = BN;
+    } else {
+        const int h = tile - p.split_from;
+        const int big = p.split_from + (h >> 1);
+        t.m0 = (big % p.num_m_blocks) * BM;
+        t.n0 = (big / p.num_m_blocks) * BN + (h & 1) * (BN / 2);
+        t.width = BN / 2;
+    }
+    return t;
+}
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -62,7 +87,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int num_tiles = p.num_tiles;
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -89,13 +114,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile % p.num_m_blocks) * BM;
-                const int n0 = (tile / p.num_m_blocks) * BN;
+                const TileCoord tc = tile_coord<BN>(p, tile);
+                const int m0 = tc.m0, n0 = tc.n0;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * C::STAGE_BYTES;
                     uint8_t* sB = sA + C::A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[stage], C::A_BYTES + tc.width * BK * 2);
                     if (!A_MN) {
                         tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m0);
                     } else {
@@ -103,12 +128,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int i = 0; i < BM / 64; ++i)
                             tma_load_2d(sA + i * (BK * 128), &tmA, &full_bar[stage], m0 + i * 64, kb * BK);
                     }
-                    if (!B_MN) {
-                        tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n0);
+                    if (!B_MN) {    // boxes of 128 rows: one per half tile
+#pragma unroll
+                        for (int i = 0; i < BN / 128; ++i)
+                            if (i * 128 < tc.width)
+                                tma_load_2d(sB + i * (128 * BK * 2), &tmB, &full_bar[stage], kb * BK, n0 + i * 128);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BN / 64; ++i)
-                            tma_load_2d(sB + i * (BK * 128), &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
+                            if (i * 64 < tc.width)
+                                tma_load_2d(sB + i * (BK * 128), &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -117,7 +146,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (warp_idx == 1) {
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            constexpr uint32_t idesc_full = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            constexpr uint32_t idesc_half = make_idesc_bf16(BM, BN / 2, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
             // K-major: 8-row groups 1024 B apart. MN-major: 64-element chunks one TMA box (BK*128 B) apart,
             // 8-row K groups 1024 B apart.
             constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0, B_LBO = B_MN ? BK * 128 : 0;
@@ -128,6 +158,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
+                const uint32_t idesc = tile < p.split_from ? idesc_full : idesc_half;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -157,12 +188,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int q = warp_idx & 3;             // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;          // row within the tile
         constexpr int EPI_COLS = OUT_F32 ? 32 : 64;
-        constexpr int NCHUNK = BN / EPI_COLS;
         const bool n_vec_ok = (p.N % 8) == 0;   // whole 16-byte groups are either inside or outside [0, N)
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile % p.num_m_blocks) * BM;
-            const int n0 = (tile / p.num_m_blocks) * BN;
+            const TileCoord tc = tile_coord<BN>(p, tile);
+            const int m0 = tc.m0, n0 = tc.n0;
+            const int nchunk = tc.width / EPI_COLS;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aphase);
@@ -171,7 +202,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const bool row_ok = grow < p.M;
             float tmax = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < NCHUNK; ++c) {
+            for (int c = 0; c < nchunk; ++c) {
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * EPI_COLS;
                 uint32_t r[EPI_COLS];
                 {
@@ -183,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 tmem_ld_wait();
-                if (c == NCHUNK - 1) {
+                if (c == nchunk - 1) {
                     // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[as]);
@@ -329,7 +360,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
         if (e != cudaSuccess) return cvh::fail_cuda("cv_gemm_bf16", e);
         attr_set = true;
     }
-    int tiles = p.num_m_blocks * p.num_n_blocks;
+    int tiles = p.num_tiles;
     int grid = tiles < cvh::num_sms() ? tiles : cvh::num_sms();
     kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, p);
     cudaError_t e = cudaGetLastError();
@@ -355,6 +386,14 @@ int dispatch(int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA, const CUte
 
 }  // namespace
 
+static bool split_tail_enabled() {   // COGVIEW_B200_GEMM_SPLIT_TAIL=0 disables tail-wave splitting (A/B measurements)
+    static const bool on = [] {
+        const char* e = getenv("COGVIEW_B200_GEMM_SPLIT_TAIL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
                      void* Cout, int c_is_f32, int64_t ldc, void* C2, const void* bias, int act, float* absmax,
                      int M, int N, int K, int block_n, const cvh::HostDropout& hd, void* stream) {
@@ -375,13 +414,15 @@ static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, 
         // Estimated time = waves x per-tile cost.  A 128x128 tile needs as many shared-memory operand bytes per
         // MMA cycle as the SM can deliver (128 B/clk), so it runs at ~2/3 of the 128x256 tile's per-column rate
         // (measured: ~0.9 vs ~1.4 PFLOP/s): cost 192 vs 256 per tile.
+        // With tail-wave splitting (tile_coord) the last partial wave of the 256-wide schedule costs one 128-wide
+        // tile when its tiles fit twice on the SMs.
         const int sms = cvh::num_sms();
         const int mb = (M + BM - 1) / BM;
-        auto waves = [&](int bn) {
-            long tiles = (long)mb * ((N + bn - 1) / bn);
-            return (tiles + sms - 1) / sms;
-        };
-        BN = (waves(128) * 192 < waves(256) * 256) ? 128 : 256;
+        const long t128 = (long)mb * ((N + 127) / 128), t256 = (long)mb * ((N + 255) / 256);
+        const long cost128 = (t128 + sms - 1) / sms * 192;
+        const long r256 = t256 % sms;
+        const long cost256 = t256 / sms * 256 + (r256 == 0 ? 0 : (2 * r256 <= sms ? 192 : 256));
+        BN = cost128 < cost256 ? 128 : 256;
     }
     CV_REQUIRE(BN == 128 || BN == 256, "block_n must be 0 (auto), 128 or 256");
 
@@ -390,6 +431,13 @@ static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, 
     p.num_m_blocks = (M + BM - 1) / BM;
     p.num_n_blocks = (N + BN - 1) / BN;
     p.num_k_blocks = (K + BK - 1) / BK;
+    {
+        const int tiles = p.num_m_blocks * p.num_n_blocks, sms = cvh::num_sms();
+        const int r = tiles % sms;
+        const int nsplit = (BN == 256 && split_tail_enabled() && r > 0 && 2 * r <= sms) ? r : 0;
+        p.split_from = tiles - nsplit;
+        p.num_tiles = tiles + nsplit;
+    }
     p.bias = static_cast<const __nv_bfloat16*>(bias);
     p.act = act;
     p.absmax = absmax;
@@ -410,7 +458,7 @@ static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, 
                     : cvh::encode_tmap_2d_bf16(&tmA, A, M, K, lda, BM, BK);
     if (rc) return rc;
     rc = b_mn_major ? cvh::encode_tmap_2d_bf16(&tmB, B, K, N, ldb, BK, 64)
-                    : cvh::encode_tmap_2d_bf16(&tmB, B, N, K, ldb, BN, BK);
+                    : cvh::encode_tmap_2d_bf16(&tmB, B, N, K, ldb, 128, BK);   // 128-row boxes: BN / 128 per stage
     if (rc) return rc;
     if (BN == 256) return dispatch<256>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, p, s);
     return dispatch<128>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, p, s);

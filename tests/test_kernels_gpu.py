@@ -44,6 +44,28 @@ def test_gemm_matches_fp32_matmul(ops, M, N, K, a_mn, b_mn):
     assert rel_err(out32, ref) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(200, 328, 136, 0, 0), (384, 640, 192, 0, 1), (320, 1000, 256, 1, 1),
+                                             (4352, 2560, 512, 0, 0), (4352, 2560, 512, 0, 1), (2560, 2560, 1088, 1, 1),
+                                             (19000, 512, 128, 0, 0)])
+def test_gemm_tail_wave_split(ops, M, N, K, a_mn, b_mn):
+    """256-wide tile schedule whose last partial wave is issued as half-width tiles (gemm.cu tile_coord): small
+    shapes (every tile split, ragged N with a fully out-of-range half), the 4B layer shapes (2 full waves + 44 split
+    tiles) and a shape with many full waves before the split tail; bf16 and fp32 outputs, all operand layouts."""
+    g = torch.Generator().manual_seed(M + N + K + a_mn)
+    A = bf(torch.randn((K, M) if a_mn else (M, K), generator=g))
+    B = bf(torch.randn((K, N) if b_mn else (N, K), generator=g))
+    bias = bf(torch.randn(N, generator=g))
+    ref = (A.float().t() if a_mn else A.float()) @ (B.float() if b_mn else B.float().t()) + bias.float()
+    for dt, tol in ((torch.bfloat16, 1e-2), (torch.float32, 1e-4)):
+        out = ops.gemm(A.cuda(), B.cuda(), a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), bias=bias.cuda(),
+                       out_dtype=dt, block_n=256)
+        diff = (out.float().cpu() - ref).abs()
+        assert diff.max().item() / ref.abs().max().item() < tol
+        # every 128 x 128 block individually (a dropped half tile in a corner must not hide behind a global max)
+        blk = torch.nn.functional.max_pool2d(diff[None, None], 128, ceil_mode=True)[0, 0]
+        assert (blk < tol * ref.abs().max()).all()
+
+
 def test_gemm_gelu_preact_absmax(ops):
     g = torch.Generator().manual_seed(3)
     A, B, bias = bf(torch.randn((384, 256), generator=g)), bf(torch.randn((1024, 256), generator=g) * 0.1), bf(
