@@ -17,6 +17,8 @@ import math
 import os
 import random
 
+import weakref
+
 import torch
 
 from .. import ops
@@ -85,10 +87,12 @@ def mask_to_sep(attention_mask, sq, sk):
         return attention_mask
     if attention_mask.numel() == 1:
         return int(attention_mask.item())
+    # The check below reads the mask back (one sync); cache the verdict per live tensor object.  The entry holds a
+    # weak reference: a new tensor that happens to reuse a freed mask's address must not inherit its verdict.
     key = (attention_mask.data_ptr(), tuple(attention_mask.shape), attention_mask._version, sq, sk)
     hit = _mask_cache.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is attention_mask:
+        return hit[1]
     m = attention_mask.reshape(-1, attention_mask.shape[-2], attention_mask.shape[-1])
     if m.shape[0] != 1 or m.shape[1] != sq or m.shape[2] != sk:
         raise ValueError('attention_mask must be [1, 1, %d, %d] or an int sep; got %s' % (sq, sk,
@@ -106,7 +110,7 @@ def mask_to_sep(attention_mask, sq, sk):
         sep = 0
     if len(_mask_cache) > 64:
         _mask_cache.clear()
-    _mask_cache[key] = sep
+    _mask_cache[key] = (weakref.ref(attention_mask), sep)
     return sep
 
 
