@@ -306,6 +306,7 @@ ln_pair_kernel(const float* __restrict__ res_in, const __nv_bfloat16* __restrict
 // decode attention
 // ------------------------------------------------------------------------------------------------
 constexpr int DA_WARPS = 4;
+constexpr int DA_UNROLL = 4;      // key blocks (of 16) in flight per CTA iteration
 constexpr int HD = 64;
 
 struct DecodeParams {
@@ -333,12 +334,10 @@ attn_decode_kernel(const DecodeParams p) {
     pdl_wait();
     const int t = p.cur_len_dev ? *p.cur_len_dev : p.cur_len;   // cached tokens; the new token sits at index t
     const __nv_bfloat16* qrow = p.qkv + (size_t)batch * 3 * h + head * HD + sub * 8;
-    float q[8], kn[8], vn[8];
+    float q[8];
     bf16x8_to_float(*reinterpret_cast<const uint4*>(qrow), q);
     const uint4 knew = *reinterpret_cast<const uint4*>(qrow + h);
     const uint4 vnew = *reinterpret_cast<const uint4*>(qrow + 2 * h);
-    bf16x8_to_float(knew, kn);
-    bf16x8_to_float(vnew, vn);
     __nv_bfloat16* kbase = p.cache + (size_t)batch * p.cache_bs + head * HD + sub * 8;
     // append (one split does it; the values are also used straight from registers below)
     if (split == p.nsplit - 1 && warp == 0 && grp == 0 && t < p.max_len) {
@@ -351,36 +350,54 @@ attn_decode_kernel(const DecodeParams p) {
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // the trip count is warp-uniform (the shuffles below need all 32 lanes); out-of-range keys are skipped
-    for (int jb = j0 + warp * 4; jb < j1; jb += DA_WARPS * 4) {
-        const int j = jb + grp;
-        const bool valid = j < j1;
-        float kf[8], vf[8];
-        if (!valid) {
+    // DA_UNROLL x 16 keys per CTA iteration: all loads of a block are issued before any is used (the loop is bound
+    // by DRAM latency otherwise: one dependent 128-byte K and V fetch per key), and the online-softmax rescale runs
+    // once per block.  The trip count is warp-uniform (the shuffles need all 32 lanes); out-of-range keys score -inf.
+    for (int jb = j0 + warp * 4; jb < j1; jb += DA_WARPS * 4 * DA_UNROLL) {
+        uint4 kr[DA_UNROLL], vr[DA_UNROLL];
+        bool valid[DA_UNROLL];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
-        } else if (j == t) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { kf[i] = kn[i]; vf[i] = vn[i]; }
-        } else {
-            const __nv_bfloat16* kp = kbase + (size_t)j * 2 * h;
-            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(kp)), kf);
-            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(kp + h)), vf);
+        for (int u = 0; u < DA_UNROLL; ++u) {
+            const int j = jb + u * DA_WARPS * 4 + grp;
+            valid[u] = j < j1;
+            kr[u] = knew;
+            vr[u] = vnew;
+            if (valid[u] && j != t) {
+                const __nv_bfloat16* kp = kbase + (size_t)j * 2 * h;
+                kr[u] = __ldg(reinterpret_cast<const uint4*>(kp));
+                vr[u] = __ldg(reinterpret_cast<const uint4*>(kp + h));
+            }
         }
-        float s = 0.f;
+        float sc[DA_UNROLL];
+        float mn = m;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(q[i], kf[i], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (valid) {
-            s *= p.scale_log2;
-            const float mn = fmaxf(m, s);
-            const float alpha = exp2f(m - mn), pr = exp2f(s - mn);
+        for (int u = 0; u < DA_UNROLL; ++u) {
+            float kf[8];
+            bf16x8_to_float(kr[u], kf);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fmaf(q[i], kf[i], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            sc[u] = valid[u] ? s * p.scale_log2 : -INFINITY;
+            mn = fmaxf(mn, sc[u]);
+        }
+        if (mn > -INFINITY) {                       // at least one key seen so far by this lane group
+            const float alpha = exp2f(m - mn);      // m = -inf on the first block -> 0
             m = mn;
-            l = l * alpha + pr;
+            l *= alpha;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = acc[i] * alpha + pr * vf[i];
+            for (int i = 0; i < 8; ++i) acc[i] *= alpha;
+#pragma unroll
+            for (int u = 0; u < DA_UNROLL; ++u) {
+                const float pr = exp2f(sc[u] - mn); // -inf -> 0
+                float vf[8];
+                bf16x8_to_float(vr[u], vf);
+                l += pr;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
+            }
         }
     }
     // combine the 16 (warp, group) partial states through shared memory

@@ -287,3 +287,25 @@ def test_attn_gather_matches_sparse_attention_inference(ops, golden_dir):
     out = sparse_attention_inference(qb[:, :, -sq:].cuda(), kb.cuda(), vb.cuda(), pw.cuda())
     assert rel_err(out, ref) < 1e-2
     assert np.abs(out.float().cpu().numpy() - g["sparse_infer"]).max() < 2e-2 * np.abs(g["sparse_infer"]).max()
+
+
+@pytest.mark.parametrize("b,heads,t,nsplit", [(2, 3, 0, 1), (2, 3, 0, 4), (1, 2, 5, 16), (3, 2, 63, 1), (2, 4, 64, 3),
+                                              (2, 2, 257, 8), (1, 40, 1087, 8)])
+def test_attn_decode_kernel_matches_softmax_attention(ops, b, heads, t, nsplit):
+    """One query per sequence over t cached keys + the appended one (mpu/sparse_transformer.py:652-673 with the
+    mems of :617-634), every key-range split count including splits that receive no key."""
+    g = torch.Generator().manual_seed(t + nsplit)
+    h, max_len = heads * 64, 1089
+    qkv = bf(torch.randn((b, 3 * h), generator=g))
+    cache = bf(torch.randn((b, max_len, 2 * h), generator=g))
+    cache_dev = cache.cuda()
+    out = ops.attn_decode(qkv.cuda(), cache_dev, heads, cur_len=t, nsplit=nsplit)
+    # the kernel appended the new K | V at position t
+    assert torch.equal(cache_dev[:, t].cpu(), qkv[:, h:])
+    assert torch.equal(cache_dev[:, :t].cpu(), cache[:, :t])
+    q = qkv[:, :h].float().view(b, heads, 1, 64)
+    kv = torch.cat((cache[:, :t].float(), qkv[:, None, h:].float()), dim=1)              # [b, t+1, 2h]
+    k = kv[..., :h].view(b, t + 1, heads, 64).permute(0, 2, 1, 3)
+    v = kv[..., h:].view(b, t + 1, heads, 64).permute(0, 2, 1, 3)
+    ref = torch.matmul(torch.softmax(torch.matmul(q / 8.0, k.transpose(-1, -2)), -1), v).reshape(b, h)
+    assert rel_err(out, ref) < 1e-2
