@@ -189,6 +189,24 @@ def filling_sequence(model, seq, args, mems=None, invalid_slices=[], **kwargs):
             continue
         else:
             assert tokens.shape[1] == counter + 1
+            # A stretch of identical 'generate' slots: run it with the sampling tail inside the decode graph (no host
+            # work per token).  Same operations as the loop body below; falls through when it does not apply.
+            run = 1
+            while counter + 1 + run < out_seq_length and tmpl[counter + 1 + run] == nxt:
+                run += 1
+            first_pos = counter - offset if counter > offset else counter
+            if (run >= 2 and index == counter and tokens.shape[0] == -nxt and args.top_p == 0.0 and is_sparse == 0
+                    and not (counter <= offset < counter + run) and hasattr(model, 'generate_run')):
+                res = model.generate_run(tokens[:, counter:], first_pos, mems, run, args.temperature, args.top_k,
+                                         invalid_slices)
+                if res is not None:
+                    new_tokens, logp, mems = res
+                    if -nxt > 1:
+                        score = (score if torch.is_tensor(score) else torch.tensor(score, device=device)) + logp
+                    tokens = torch.cat((tokens, new_tokens), dim=1)
+                    counter += run
+                    index = counter
+                    continue
             position_ids = torch.arange(index, counter + 1, dtype=torch.long, device=device).unsqueeze(0)
             position_ids[position_ids > offset] -= offset
             tokens, mems, score = shrink_beams(tokens, mems, -nxt, score)

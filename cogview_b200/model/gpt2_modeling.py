@@ -135,6 +135,35 @@ def _fast_decode_impl(self, input_ids, position_ids, mems, b, sq):
 GPT2Model._fast_decode = _fast_decode_impl
 
 
+def _generate_run_impl(self, last_tokens, first_pos, mems, n_steps, temperature, top_k, invalid_slices):
+    """n_steps sampled tokens in a row on the K|V cache — the inner loop of generation/sampling.py:147-183 for a
+    stretch of the template that is all 'generate' slots — with the sampling tail inside the replayed CUDA graph
+    (mpu/decode.py sample_run).  Returns None when the fast path does not apply, else
+    (tokens [b, n_steps], summed log-probabilities [b], mems)."""
+    tr = self.transformer
+    b = last_tokens.shape[0]
+    if (not mems or tr.mems_mode != 'kv' or tr.max_memory_length <= 0 or torch.is_grad_enabled() or b > 16
+            or n_steps < 1 or os.environ.get('COGVIEW_B200_FAST_DECODE', '1') == '0'
+            or os.environ.get('COGVIEW_B200_GRAPH_SAMPLING', '1') == '0'):
+        return None
+    from ..mpu import kv_cache
+    from ..mpu.decode import DecodeRunner
+    if mems[0].size(1) + n_steps > tr.max_memory_length:
+        return None
+    caches = kv_cache.prepare(tr, mems, b, n_steps)
+    runner = getattr(caches, 'runner', None)
+    if runner is None:
+        runner = caches.runner = DecodeRunner(self, caches,
+                                              use_graph=os.environ.get('COGVIEW_B200_CUDA_GRAPH', '1') != '0')
+    pos = torch.full((b, 1), int(first_pos), dtype=torch.long, device=last_tokens.device)
+    new_tokens, logp = runner.sample_run(last_tokens.reshape(b, 1), pos, caches.t, n_steps, temperature, top_k,
+                                         invalid_slices)
+    return new_tokens, logp, caches.views()
+
+
+GPT2Model.generate_run = _generate_run_impl
+
+
 class _NoCtx:
     def save_for_backward(self, *a):
         pass

@@ -6,6 +6,7 @@ abs-max LN -> QKV linear -> cached attention (+ append) -> out-proj (+abs-max) -
 h->4h (+GELU) -> 4h->h (+abs-max) -> LN + residual, all weight-streaming kernels (cv_linear_small_m,
 cv_attn_decode) with the position read from device memory so the graph is replayable."""
 import torch
+import torch.nn.functional as F
 
 from .. import ops
 from .layers import _as_bf16
@@ -34,6 +35,11 @@ class DecodeRunner:
         self.params = None
         self.graph_launches = 0   # kernels per captured step
         self.replays = 0
+        # token-generation runs (model step + sampling in one graph, next token fed back on the device)
+        self.sample_graphs = {}
+        self.out_buf = torch.zeros((self.b, caches.maxlen + 1), dtype=torch.int64, device=dev)
+        self.stepc = torch.zeros((1, 1), dtype=torch.int64, device=dev)
+        self.score_acc = torch.zeros(self.b, dtype=torch.float32, device=dev)
 
     def _gather_params(self):
         tr = self.model.transformer
@@ -98,3 +104,70 @@ class DecodeRunner:
             self.graph.replay()
             self.replays += 1
         return self.logits
+
+    # -- generation runs: generation/sampling.py:147-183 with nothing left on the host per token -----------------
+    def _sample_body(self, key):
+        """One token: decode step, then the reference's sampling tail — temperature, invalid vocabulary slices,
+        top-k (generation/sampling.py:24-33 with the boolean index_put written as the equivalent masked_fill so that
+        it can be captured), softmax, torch.multinomial, beam log-probability — and the hand-over of the sampled
+        token to the next step, all through device-side state."""
+        temperature, top_k, inv = key
+        self._run()
+        logits = self.logits
+        logits.div_(temperature)
+        for a, z in inv:
+            logits[:, a:z] = -float('Inf')
+        if top_k > 0:
+            kth = torch.topk(logits, top_k)[0][..., -1, None]
+            logits.masked_fill_(logits < kth, -float('Inf'))
+        probs = F.softmax(logits, dim=-1)
+        prev = torch.multinomial(probs, num_samples=1)
+        self.score_acc.add_(torch.log(torch.gather(probs, 1, prev)[:, 0]))
+        self.out_buf.scatter_(1, self.stepc.expand(self.b, 1), prev)
+        self.stepc.add_(1)
+        self.ids.copy_(prev)
+        self.pos.add_(1)
+        self.cur_len.add_(1)
+
+    def _reset_run(self, ids, pos, t):
+        self.ids.copy_(ids)
+        self.pos.copy_(pos)
+        self.cur_len.fill_(t)
+        self.stepc.zero_()
+        self.score_acc.zero_()
+
+    def sample_run(self, ids, pos, t, n_steps, temperature, top_k, invalid_slices):
+        """n_steps tokens starting from `ids` ([b, 1], at positions `pos`, t tokens cached).  One graph replay per
+        token.  Returns (tokens [b, n_steps] int64, summed log-probabilities [b] fp32)."""
+        if self.params is None:
+            self._gather_params()
+        vocab = self.model.word_embeddings.weight.shape[0]
+        key = (float(temperature), int(top_k), tuple(sl.indices(vocab)[:2] for sl in invalid_slices))
+        assert n_steps <= self.out_buf.shape[1]
+        self._reset_run(ids, pos, t)
+        graph = self.sample_graphs.get(key)
+        if graph is None and self.use_graph:
+            dev = self.ids.device
+            rng = torch.cuda.get_rng_state(dev)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):           # warm-up (allocator, lazy init); its side effects are undone below
+                self._sample_body(key)
+                self._sample_body(key)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.set_rng_state(rng, dev)
+            self._reset_run(ids, pos, t)
+            from .._lib import lib
+            before = lib().cv_launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._sample_body(key)
+            self.graph_launches = int(lib().cv_launch_count() - before)   # this library's kernels per replayed token
+            self.sample_graphs[key] = graph
+        for _ in range(n_steps):
+            if graph is None:
+                self._sample_body(key)
+            else:
+                graph.replay()
+        self.replays += n_steps
+        return self.out_buf[:, :n_steps].clone(), self.score_acc.clone()

@@ -191,3 +191,38 @@ def test_sparse_inference_equals_dense_when_window_covers_everything(data):
             p = torch.full((2, 1), t, dtype=torch.long, device="cuda")
             lg_s, *mems_s = m(nxt, p, 0, ~img, img, 2, *mems_s)
         assert mems_s[0].size(1) == 68 and bool(torch.isfinite(lg_s).all())
+
+
+def _fill(monkeypatch, graph_sampling, top_k, seed):
+    """filling_sequence (generation/sampling.py:64-186) on the tiny model: 20 context tokens, 44 generated, 3 beams."""
+    from cogview_b200.generation import sampling
+    monkeypatch.setenv("COGVIEW_B200_GRAPH_SAMPLING", "1" if graph_sampling else "0")
+    m = build(max_memory_length=CFG["max_sequence_length"], mems_mode="kv").eval()
+
+    class A:
+        temperature, top_p, is_sparse = 1.0, 0.0, 0
+        img_tokenizer_num_tokens = recipes.IMG_VOCAB
+    A.top_k = top_k
+
+    tok = sampling.get_tokenizer(A)
+    g = torch.Generator().manual_seed(3)
+    text = torch.randint(recipes.IMG_VOCAB, recipes.IMG_VOCAB + 100, (18,), generator=g).tolist()
+    seq = [tok['[ROI1]']] + text + [tok['[BASE]'], tok['[BOI1]']] + [-3] * 44
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        out = sampling.filling_sequence(m, torch.tensor(seq, dtype=torch.long, device="cuda"), A)
+    return out.cpu(), len(seq)
+
+
+def test_filling_sequence_graph_sampling_matches_eager_loop(monkeypatch):
+    """The generation run with the sampling tail inside the decode graph (mpu/decode.py sample_run) against the
+    per-token host loop: identical tokens for top-k = 1 (no randomness left), valid image codes for top-k = 200."""
+    eager, n = _fill(monkeypatch, False, 1, 0)
+    fused, _ = _fill(monkeypatch, True, 1, 0)
+    assert eager.shape == fused.shape == (3, n)
+    assert torch.equal(eager[:, :21], fused[:, :21])
+    agree = (eager == fused).float().mean().item()
+    assert agree == 1.0, agree
+    sampled, _ = _fill(monkeypatch, True, 200, 1)
+    assert sampled.shape == (3, n) and int(sampled[:, 21:].min()) >= 0 and int(sampled[:, 21:].max()) < recipes.IMG_VOCAB
+    assert len({tuple(r.tolist()) for r in sampled[:, 21:]}) > 1          # beams diverge
