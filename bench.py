@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--gen-tokens", type=int, default=1024)
     ap.add_argument("--model", default="4b", choices=["4b", "tiny"])
     ap.add_argument("--train-steps", type=int, default=None)
+    ap.add_argument("--skip-cpu-baseline", action="store_true",
+                    help="development only: leave out the host-core baseline leg (the default run includes it)")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="embedding/attention/hidden dropout of the training workload (reference scripts: 0.1)")
     return ap.parse_args()
@@ -600,7 +602,10 @@ def main():
                         e2e=t["e2e"], clocks=t["clocks"], gpu_launches=t["gpu_launches"], roofline=t["roofline"],
                         config=t["config"], steps=t["steps"], warmup=t["warmup"])
         line["train"] = t
-    if rank == 0:
+    if rank == 0 and args.skip_cpu_baseline:        # development runs only: the contract line carries cpu_baseline
+        line["cpu_baseline"] = None
+        print(json.dumps(line))
+    elif rank == 0:
         if args.workload in ("sample", "both", "all"):
             line["cpu_baseline"] = cpu_baseline_sample(cfg, args.batch, args.gen_tokens)
         if args.workload in ("vqvae", "all"):
