@@ -8,8 +8,6 @@
 //   cv_attn_decode    : one query per sequence against the K|V cache, with the new token's K/V appended
 //                       in the same kernel (standard_attention, mpu/sparse_transformer.py:652-673, for sq = 1,
 //                       where every cached key is visible)
-#include <cstdlib>
-
 #include "common.cuh"
 #include "host.h"
 #include "../../include/cogview_b200.h"
@@ -32,7 +30,6 @@ using namespace cv;
 constexpr int SK_WARPS = 8;
 constexpr int SK_NT = 16;         // output columns per CTA
 constexpr int SK_UNROLL = 8;      // K chunks (of 32) in flight per warp: 512 contiguous bytes of each of its 16 rows
-constexpr bool LINEAR_STREAM_DEFAULT = false;   // linear_small_m_stream_kernel: opt-in until measured
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -163,127 +160,6 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
     if (!waited) {       // empty column range: still take part in the launch chain
         pdl_launch_dependents();
         pdl_wait();
-    }
-    if (absmax != nullptr && warp < 4) {
-        tmax = warp_max(tmax);
-        if (lane == 0 && tmax > 0.f) atomic_max_nonneg(absmax, tmax);
-    }
-}
-
-// Same partition and fragment scheme, but the K chunks of ALL the CTA's column tiles form one stream per warp: slot u
-// of the register ring is refilled with the next (tile, chunk) item as soon as it has been consumed, so the loads of
-// the next tile are already in flight while the current tile is reduced and written — with K = 2560 a warp has only
-// 10 chunks per tile, and restarting the pipeline per tile (kernel above) exposes the DRAM latency twice per tile.
-// Every warp walks the same number of items (chunks beyond its K range are zero items), which keeps the per-tile
-// barrier in uniform control flow.
-__global__ void __launch_bounds__(SK_WARPS * 32, 2)
-linear_small_m_stream_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ W,
-                             int64_t ldw, const __nv_bfloat16* __restrict__ bias, void* __restrict__ out, int64_t ldo,
-                             int out_f32, int act, float* __restrict__ absmax, int M, int N, int K) {
-    __shared__ float part[2][SK_WARPS][SK_NT][8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, q = lane & 3;
-    const int c_lo = (int)(((int64_t)N * blockIdx.x) / gridDim.x);
-    const int c_hi = (int)(((int64_t)N * (blockIdx.x + 1)) / gridDim.x);
-    const int nchunks = (K + 31) / 32;
-    const int nck = (nchunks + SK_WARPS - 1) / SK_WARPS;          // items per tile, the same for every warp
-    const int c_begin = warp * nck, c_end = min(nchunks, c_begin + nck);
-    const int ntiles = (c_hi - c_lo + SK_NT - 1) / SK_NT;
-    const int nitems = ntiles * nck;
-    const bool x_ok = g < M;
-    const __nv_bfloat16* xrow = x + (size_t)g * ldx + q * 8;
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    const uint64_t pol = make_evict_first_policy();
-
-    // load cursor: item li = (tile lt, chunk offset lc)
-    int li = 0, lt = 0, lc = 0;
-    const __nv_bfloat16* lw0 = W + (size_t)(c_lo + g) * ldw + q * 8;
-    const __nv_bfloat16* lw1 = lw0 + (size_t)8 * ldw;
-    bool lr0 = c_lo + g < c_hi, lr1 = c_lo + g + 8 < c_hi;
-    SkStage st;
-    auto load_w = [&](int u) {
-        const int c = c_begin + lc;
-        const bool in = li < nitems && c < c_end && c * 32 + q * 8 < K;
-        st.w0[u] = (in && lr0) ? ld_stream(lw0 + (size_t)c * 32, pol) : zero;
-        st.w1[u] = (in && lr1) ? ld_stream(lw1 + (size_t)c * 32, pol) : zero;
-    };
-    auto load_x = [&](int u) {
-        const int c = c_begin + lc;
-        const bool in = li < nitems && c < c_end && c * 32 + q * 8 < K;
-        st.xv[u] = (in && x_ok) ? *reinterpret_cast<const uint4*>(xrow + (size_t)c * 32) : zero;
-    };
-    auto advance_load = [&]() {
-        ++li;
-        if (++lc == nck) {
-            lc = 0;
-            ++lt;
-            const int n0 = c_lo + lt * SK_NT;
-            lw0 = W + (size_t)(n0 + g) * ldw + q * 8;
-            lw1 = lw0 + (size_t)8 * ldw;
-            lr0 = n0 + g < c_hi;
-            lr1 = n0 + g + 8 < c_hi;
-        }
-    };
-
-    // prologue: the weights of the first SK_UNROLL items do not depend on the previous kernel — request them, let the
-    // next kernel start its own prologue, then wait for the producer of x and fetch x for the same items
-    {
-        const int li0 = li, lt0 = lt, lc0 = lc;
-        const __nv_bfloat16 *a0 = lw0, *a1 = lw1;
-        const bool b0 = lr0, b1 = lr1;
-#pragma unroll
-        for (int u = 0; u < SK_UNROLL; ++u) { load_w(u); advance_load(); }
-        pdl_launch_dependents();
-        pdl_wait();
-        li = li0; lt = lt0; lc = lc0; lw0 = a0; lw1 = a1; lr0 = b0; lr1 = b1;
-#pragma unroll
-        for (int u = 0; u < SK_UNROLL; ++u) { load_x(u); advance_load(); }
-    }
-
-    float tmax = 0.f;
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-    int ct = 0, cc = 0, buf = 0;                                   // consume cursor: tile, chunk offset
-    for (int base = 0; base < nitems; base += SK_UNROLL) {
-#pragma unroll
-        for (int u = 0; u < SK_UNROLL; ++u) {
-            if (base + u < nitems) {                              // uniform over the CTA
-                mma_bf16_16816(d, st.w0[u].x, st.w1[u].x, st.w0[u].y, st.w1[u].y, st.xv[u].x, st.xv[u].y);
-                mma_bf16_16816(d, st.w0[u].z, st.w1[u].z, st.w0[u].w, st.w1[u].w, st.xv[u].z, st.xv[u].w);
-                load_w(u);                                        // refill the slot with item base + u + SK_UNROLL
-                load_x(u);
-                advance_load();
-                if (++cc == nck) {                                // this tile's K range is complete for every warp
-                    cc = 0;
-                    part[buf][warp][g][2 * q] = d[0];
-                    part[buf][warp][g][2 * q + 1] = d[1];
-                    part[buf][warp][g + 8][2 * q] = d[2];
-                    part[buf][warp][g + 8][2 * q + 1] = d[3];
-                    d[0] = d[1] = d[2] = d[3] = 0.f;
-                    __syncthreads();
-                    if (threadIdx.x < SK_NT * 8) {
-                        const int m = threadIdx.x >> 4, nn = threadIdx.x & 15;
-                        float v = 0.f;
-#pragma unroll
-                        for (int w = 0; w < SK_WARPS; ++w) v += part[buf][w][nn][m];
-                        const int n = c_lo + ct * SK_NT + nn;
-                        if (m < M && n < c_hi) {
-                            if (bias != nullptr) v += __bfloat162float(bias[n]);
-                            if (act == 1) v = gelu_tanh(v);
-                            if (out_f32) {
-                                static_cast<float*>(out)[(size_t)m * ldo + n] = v;
-                                tmax = fmaxf(tmax, fabsf(v));
-                            } else {
-                                const __nv_bfloat16 o = __float2bfloat16_rn(v);
-                                static_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + n] = o;
-                                tmax = fmaxf(tmax, fabsf(__bfloat162float(o)));
-                            }
-                        }
-                    }
-                    buf ^= 1;
-                    ++ct;
-                }
-            }
-        }
     }
     if (absmax != nullptr && warp < 4) {
         tmax = warp_max(tmax);
@@ -669,14 +545,9 @@ extern "C" int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int6
     const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(bias);
     const size_t osz = out_is_f32 ? 4 : 2;
     // the MMA N dimension holds up to 8 batch rows; 9..16 rows take a second pass over the weights
-    static const bool stream_variant = [] {      // COGVIEW_B200_LINEAR_STREAM=1/0: cross-tile load pipelining
-        const char* e = getenv("COGVIEW_B200_LINEAR_STREAM");
-        return e ? e[0] != '0' : LINEAR_STREAM_DEFAULT;
-    }();
     for (int m0 = 0; m0 < M; m0 += 8) {
         const int mm = (M - m0) < 8 ? (M - m0) : 8;
-        CV_CUDA(cvh::launch_pdl(stream_variant ? linear_small_m_stream_kernel : linear_small_m_kernel, dim3(grid),
-                                dim3(SK_WARPS * 32), 0, s, true,
+        CV_CUDA(cvh::launch_pdl(linear_small_m_kernel, dim3(grid), dim3(SK_WARPS * 32), 0, s, true,
                                 xb + (size_t)m0 * ldx, ldx, wb, ldw, bb,
                                 static_cast<void*>(static_cast<char*>(out) + (size_t)m0 * ldo * osz), ldo, out_is_f32,
                                 act, absmax, mm, N, K));
