@@ -88,10 +88,14 @@ int cv_absmax(const void* x, int x_is_bf16, int64_t n, float* out, void* stream)
  *          mpu/sparse_transformer.py:477-489)
  *   out: [b, sq, heads*64] bf16 (token-major, what the out-projection GEMM reads); lse: NULL or [b, heads, sq]
  *   dropout_p > 0: dropout on the attention probabilities (torch.nn.Dropout under the RNG-tracker fork,
- *         mpu/sparse_transformer.py:667-669): one Philox4x32-10 call per (query, 128-key tile) of the counter-based
- *         generator (seed, site) seeds four 32-step LCG streams, keep iff state >= p * 2^32.  drop_mask
- *         [b, heads, ceil(sk/128)*128, ceil(sq/128), 4] uint32 receives the keep bits for the backward, key-major:
- *         bit i of word w of (key, query block qb) is query qb*128 + 32w + i.
+ *         mpu/sparse_transformer.py:667-669).  The keep decisions are generated by a separate full-occupancy kernel
+ *         launched by this call: one Philox4x32-10 call per (query, 128-key tile) of the counter-based generator
+ *         (seed, site) seeds four 32-step LCG streams, keep iff state >= p * 2^32.
+ *         drop_mask: uint32 buffer of 2 * b * heads * ceil(sk/128) * ceil(sq/128) * 128 * 4 words, two regions:
+ *           [0] key-major   [b, heads, ceil(sk/128)*128, ceil(sq/128), 4]: bit i of word w of (key, query block qb)
+ *               is query qb*128 + 32w + i — what cv_attn_bwd reads (pass the same pointer);
+ *           [1] query-major [b, heads, ceil(sq/128)*128, ceil(sk/128), 4]: consumed by the forward kernel.
+ *         Tiles that the mask never makes visible are left unwritten.
  * ---------------------------------------------------------------------------------------------- */
 int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
                 int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, float* lse, int b, int heads,
@@ -99,7 +103,7 @@ int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t 
                 uint32_t* drop_mask, void* stream);
 
 /* Backward of cv_attn_fwd for sq == sk (training).  q/k/v as in cv_attn_fwd; out, d_out: [b, s, heads*64] bf16
- * contiguous; lse from the forward.  dqkv: [b, s, 3*heads*64] bf16 (dQ | dK | dV, the layout of the packed QKV
+ * contiguous; lse from the forward; dropout_p > 0: drop_mask is the buffer the forward filled (region [0] is read).  dqkv: [b, s, 3*heads*64] bf16 (dQ | dK | dV, the layout of the packed QKV
  * GEMM output, so the QKV dgrad/wgrad GEMMs read it directly).  workspace: cv_attn_bwd_workspace_bytes(). */
 int64_t cv_attn_bwd_workspace_bytes(int b, int heads, int head_dim, int s);
 int cv_attn_bwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
