@@ -147,3 +147,27 @@ def test_weight_decay_parameter_groups():
         assert names[id(p)].endswith('bias') or 'layernorm' in names[id(p)].lower(), names[id(p)]
     for p in decay['params']:
         assert names[id(p)].endswith('weight') and 'layernorm' not in names[id(p)].lower(), names[id(p)]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) on the tiny configuration: one JSON line with
+    the contract's keys, `impl = reference`, a `cpu_baseline` describing the run and a zero-copy `e2e`."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "tiny",
+                        "--steps", "1", "--warmup", "0", "--gen-tokens", "16"], capture_output=True, text=True,
+                       timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
