@@ -110,3 +110,27 @@ def test_vqvae_matches_reference(golden_dir):
     assert np.array_equal(codes.numpy(), g["codes"])                                      # bit-exact indices
     rec = O.code2img(sd, codes.view(2, 8, 8))
     assert np.allclose(rec.numpy(), g["recon"], atol=2e-5)
+
+
+def test_sparse_training_attention_two_pass_decomposition(golden_dir):
+    """Row a7 (not yet built in CUDA): the band + pivot two-pass form with a joint log-sum-exp that a tile-scheduled
+    kernel would run (oracle/sparse_decomposition.py) reproduces the reference's sparse_attention — forward against
+    the golden output, visibility rules against the reference's rmask, backward against autograd."""
+    from oracle import sparse_decomposition as SD
+    g = _load(golden_dir, "attention.npz")
+    q, k, v, pivot_idx, pam, (b, nh, s, hn, w, times, n_piv, sq) = _attention_inputs(g)
+    band, piv = SD.visibility(s, pivot_idx, w, times)
+    assert torch.equal(piv.float(), pam)                                   # closed form == gathered rmask
+    wm = torch.tril(torch.ones(s, s)) * (1 - torch.nn.functional.pad(
+        torch.tril(1 - torch.block_diag(*torch.ones((s // w - times + 1, w, w)))), (0, (times - 1) * w, (times - 1) * w, 0)))
+    assert torch.equal(band.float(), wm)                                   # band == causal minus the pivot region
+    out, lse = SD.sparse_attention_two_pass(q, k, v, pivot_idx, w, times)
+    assert np.allclose(out.numpy()[:, :, ::7], g["sparse_train"], atol=1e-5)
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    ref = O.sparse_attention(qr, kr, vr, pivot_idx, pam, w, times)
+    gen = torch.Generator().manual_seed(11)
+    d_out = torch.randn(ref.shape, generator=gen)
+    ref.backward(d_out)
+    dq, dk, dv = SD.sparse_attention_two_pass_backward(q, k, v, pivot_idx, w, times, out, lse, d_out)
+    for got, want in ((dq, qr.grad), (dk, kr.grad), (dv, vr.grad)):
+        assert (got - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
