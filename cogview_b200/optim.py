@@ -19,6 +19,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.max_grad_norm = float(max_grad_norm)
         self._scal = None
         self._tables = None          # (pinned host staging x2, device table), rebuilt when the parameter list changes
+        self._copied = [None, None]  # CUDA event recorded after the async copy out of each staging buffer
         self._flip = 0
         self.last_grad_norm = None   # device tensor (1,) after step() when clipping is on
 
@@ -31,7 +32,10 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._tables is None or self._tables[2].numel() != n * 64 or self._tables[2].device != dev:
             host = [torch.empty(n * 64, dtype=torch.uint8).pin_memory() for _ in range(2)]
             self._tables = (host[0], host[1], torch.empty(n * 64, dtype=torch.uint8, device=dev))
+            self._copied = [None, None]
         self._flip ^= 1                                   # double-buffered: the previous step's copy may be in flight
+        if self._copied[self._flip] is not None:          # the copy issued two steps ago has long finished; make sure
+            self._copied[self._flip].synchronize()
         host = self._tables[self._flip]
         rec = host.numpy().view(self._ENTRY)
         for i, (group, p) in enumerate(plist):
@@ -42,6 +46,9 @@ class FusedAdamW(torch.optim.Optimizer):
                       st['exp_avg_sq'].data_ptr(), p.numel(), group['lr'], group['weight_decay'],
                       1.0 - b1 ** st['step'], 1.0 - b2 ** st['step'])
         self._tables[2].copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._copied[self._flip] = ev
         return self._tables[2]
 
     def _state_for(self, p):
