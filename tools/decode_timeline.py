@@ -34,8 +34,15 @@ def main():
     t0, t1 = dec[0].time_range.start, dec[-1].time_range.end
     busy = collections.defaultdict(float)
     cnt = collections.Counter()
+    def short(name):
+        name = name.replace("void ", "").replace("(anonymous namespace)::", "")
+        for cut in ("<", "("):
+            if cut in name:
+                name = name[:name.index(cut)]
+        return name.split("::")[-1][:60] or "?"
+
     for e in dec:
-        k = e.name.split("(")[0][:70]
+        k = short(e.name)
         busy[k] += e.time_range.end - e.time_range.start
         cnt[k] += 1
     # union of busy intervals (kernels overlap under PDL) and gaps
@@ -49,7 +56,7 @@ def main():
         elif en > cur_end:
             cover += en - cur_end
             cur_end = en
-    steps = max(1, cnt.get(max(cnt, key=lambda k: ("attn_decode_kernel" in k, cnt[k])), 1) // cfg["num_layers"])
+    steps = max(1, cnt.get("attn_decode_kernel", cfg["num_layers"]) // cfg["num_layers"])
     wall = t1 - t0
     print(f"decode window {wall / 1e3:.2f} ms, ~{steps} steps -> {wall / steps:.0f} us/step; "
           f"GPU covered {100 * cover / wall:.1f}%, {len(gaps)} gaps, total gap {sum(gaps) / 1e3:.2f} ms, "
