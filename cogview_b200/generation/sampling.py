@@ -9,6 +9,9 @@ Same call signatures and semantics; two host-side differences that do not change
     `tok.img_tokenizer.num_tokens`, `tok.txt_tokenizer.num_tokens`); `TokenLayout` provides that surface from
     the vocabulary sizes alone (the role FakeTokenizer plays in data_utils/unified_tokenizer.py:208-212).
 """
+import math
+
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -38,6 +41,24 @@ class TokenLayout:
 
     def __getitem__(self, command_token):
         return self.command_tokens[command_token]
+
+    def wrap_code(self, code, idx=1):
+        """data_utils/unified_tokenizer.py:125-151: [size tag] [BOIidx] code [EOIidx]; the tag follows the side of
+        the (square) code grid.  Lists, numpy arrays and tensors keep their type."""
+        n = len(code)
+        side = int(math.sqrt(n) + 1e-4)
+        assert side * side == n, 'image codes must form a square grid'
+        prefix = {8: '[TINY]', 16: '[SMALL]', 32: '[BASE]', 64: '[BIG]'}[side]
+        head = [self.command_tokens[prefix], self.command_tokens['[BOI%d]' % idx]]
+        tail = [self.command_tokens['[EOI%d]' % idx]]
+        if isinstance(code, list):
+            return head + code + tail
+        if isinstance(code, np.ndarray):
+            return np.concatenate((np.array(head), code, np.array(tail)), axis=0)
+        if isinstance(code, torch.Tensor):
+            return torch.cat((torch.tensor(head, dtype=code.dtype, device=code.device), code,
+                              torch.tensor(tail, dtype=code.dtype, device=code.device)))
+        raise ValueError('code must be a list, numpy array or tensor')
 
     def __len__(self):
         return self.num_tokens
