@@ -53,7 +53,7 @@ def _worker(rank, world, port, out):
 
 def test_dp_wrapper_and_groups_world2():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context('spawn').Manager()           # no fork() from the multi-threaded test process
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert sorted(out.keys()) == [0, 1]
