@@ -121,3 +121,42 @@ def test_magnify_window_assembly():
     assert out.shape == (1, 4096) and len(calls) == 9
     assert torch.equal(out.view(64, 64), 10000 + torch.arange(4096).view(64, 64))
     assert (generated == 1).all()
+
+
+def test_train_step_glue_with_a_stand_in_model(monkeypatch):
+    """pretrain.train_step control flow (pretrain_gpt2.py:406-450) with a CPU stand-in for the model and the oracle's
+    cross-entropy in place of the CUDA op: parameters move, the scheduler steps, and a non-finite forward skips the
+    backward / optimizer step and reports skipped_iter = 1."""
+    from cogview_b200 import pretrain
+    monkeypatch.setattr(pretrain.mpu, "vocab_parallel_cross_entropy", O.vocab_parallel_cross_entropy)
+    V, h, b, s = 8192 + 200, 16, 2, 24
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(V, h)
+            self.poison = False
+
+        def forward(self, tokens, position_ids, attention_mask, txt_bool, img_bool, is_sparse, *mems):
+            assert txt_bool.shape == img_bool.shape == tokens.shape and attention_mask.shape[-1] == tokens.shape[1]
+            x = self.emb(tokens)
+            logits = x @ self.emb.weight.t()
+            if self.poison:
+                logits = logits * float("nan")
+            return (logits,)
+    torch.manual_seed(0)
+    m = Tiny()
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.5 ** it)
+    g = torch.Generator().manual_seed(1)
+    tokens_full = torch.cat((torch.randint(8192, V, (b, 8), generator=g), torch.randint(0, 8192, (b, s - 7), generator=g)), 1)
+    from cogview_b200 import data
+    batch = data.make_batch({"text": tokens_full.numpy(), "loss_mask": np.ones((b, s + 1))})
+    w0 = m.emb.weight.detach().clone()
+    loss, skipped, mems, img_loss, txt_loss = pretrain.train_step(batch, m, opt, sched, txt_loss_scale=0.5)
+    assert skipped == 0 and torch.isfinite(loss) and mems == [] and img_loss > 0 and txt_loss > 0
+    assert not torch.equal(m.emb.weight, w0) and sched.last_epoch == 1
+    m.poison = True
+    w1 = m.emb.weight.detach().clone()
+    out, skipped, *_ = pretrain.train_step(batch, m, opt, sched, txt_loss_scale=0.5)
+    assert skipped == 1 and torch.isnan(out) and torch.equal(m.emb.weight, w1) and sched.last_epoch == 1
