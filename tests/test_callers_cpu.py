@@ -160,3 +160,53 @@ def test_train_step_glue_with_a_stand_in_model(monkeypatch):
     w1 = m.emb.weight.detach().clone()
     out, skipped, *_ = pretrain.train_step(batch, m, opt, sched, txt_loss_scale=0.5)
     assert skipped == 1 and torch.isnan(out) and torch.equal(m.emb.weight, w1) and sched.last_epoch == 1
+
+
+def test_query_templates_build_and_split_round_trip():
+    from cogview_b200 import generate as gen
+    tok = _tok()
+    text = [8192 + 10, 8192 + 11, 8192 + 12]
+    seq = gen.build_query(gen.QUERY_TEMPLATES['text2image'], [text], tok)
+    assert seq[:6] == [tok['[ROI1]']] + text + [tok['[BASE]'], tok['[BOI1]']] and seq[6:] == [-1] * 1024
+    codes = list(range(1024))
+    seq = gen.build_query(gen.QUERY_TEMPLATES['low-level super-resolution'], [text, codes], tok)
+    assert seq.count(-1) == 1024 and len(seq) == 1 + 3 + 2 + 1024 + 5 + 1024
+    assert seq[6:6 + 1024] == codes and seq[6 + 1024:6 + 1024 + 5] == [tok['[EOI1]'], tok['[ROI2]'], tok['[POS0]'],
+                                                                   tok['[BASE]'], tok['[BOI2]']]
+    half = gen.build_query('[BASE] [BOI1] [Image512]{}', [codes], tok)          # keep 512 codes, generate the rest
+    assert half[2:514] == codes[:512] and half[514:] == [-1] * 512
+    with pytest.raises(ValueError):
+        gen.build_query('[ROI1] a_raw_word [BASE]', [], tok)
+    filled = [c if c >= 0 else 7 for c in gen.build_query(gen.QUERY_TEMPLATES['post-selection'], [codes, text], tok)]
+    parts, images = gen.split_tokens(filled, tok)
+    assert images == [codes] and parts == ['[BASE]', '[BOI1]', '[EOI1]', '[ROI1]', [10, 11, 12]]
+
+
+def test_generate_images_once_batches_beams_and_decodes_the_last_image():
+    from cogview_b200 import generate as gen
+    tok = _tok()
+    seq = torch.tensor(gen.build_query(gen.QUERY_TEMPLATES['text2image'], [[8192 + 5]], tok))
+
+    class Args:
+        max_inference_batch_size = 4
+    calls = []
+
+    def fake_fill(model, s, args):
+        nb = -int(s[s < 0][0])
+        assert (s[s < 0] == -nb).all()
+        calls.append(nb)
+        rows = s.clone().unsqueeze(0).repeat(nb, 1)
+        rows[rows < 0] = len(calls)                        # "generated" code = index of the call
+        return rows
+
+    def fake_decode(codes):
+        assert codes.shape == (1, 1024)
+        return codes.float().mean().view(1, 1, 1, 1).expand(1, 3, 256, 256)
+    rows, imgs = gen.generate_images_once(torch.nn.Identity(), None, Args, seq, num=8, fill=fake_fill, decode=fake_decode)
+    assert calls == [4, 4] and rows.shape == (8, len(seq)) and imgs.shape == (8, 3, 256, 256)
+    assert imgs[:4].unique().tolist() == [1.0] and imgs[4:].unique().tolist() == [2.0]
+    assert (seq < 0).sum() == 1024                                             # the caller's template is untouched
+    rows, imgs = gen.generate_images_once(torch.nn.Identity(), None, Args, seq, num=2, fill=fake_fill, decode=fake_decode)
+    assert calls[-1] == 2 and rows.shape[0] == 2
+    with pytest.raises(AssertionError):
+        gen.generate_images_once(torch.nn.Identity(), None, Args, seq, num=6, fill=fake_fill, decode=fake_decode)
