@@ -22,6 +22,19 @@ class CogViewB200Error(RuntimeError):
     pass
 
 
+class DecodeStepArgs(ctypes.Structure):
+    """cv_decode_step_args of include/cogview_b200.h (host struct)."""
+    _fields_ = [("layers", c_void_p),
+                ("num_layers", c_int), ("hidden", c_int), ("heads", c_int), ("vocab", c_int), ("batch", c_int),
+                ("max_len", c_int),
+                ("eps", c_float), ("eps_final", c_float),
+                ("wte", c_void_p), ("wpe", c_void_p), ("lnf_g", c_void_p), ("lnf_b", c_void_p),
+                ("ids", c_void_p), ("pos", c_void_p), ("cur_len", c_void_p),
+                ("cache", c_void_p), ("cache_layer_stride", c_int64), ("cache_batch_stride", c_int64),
+                ("logits", c_void_p), ("ld_logits", c_int64),
+                ("workspace", c_void_p)]
+
+
 def _declare(lib):
     lib.cv_version.restype = c_int
     lib.cv_last_error.restype = ctypes.c_char_p
@@ -43,9 +56,9 @@ def _declare(lib):
         "cv_attn_decode": [P, P, L, P, I, P, P, I, I, I, I, I, P],
         "cv_adamw_step": [P, P, P, P, P, L, F, F, F, F, F, I, P, F, P],
         "cv_sumsq_bf16": [P, L, P, P],
-        "cv_adamw_step_multi": [P, I, F, F, F, P, F, P],
+        "cv_adamw_step_multi": [P, I, F, F, F, P, F, P, P],
         "cv_sumsq_bf16_multi": [P, I, P, P],
-        "cv_clip_coef": [P, F, P, P, P],
+        "cv_clip_coef": [P, F, P, P, P, P],
         "cv_conv2d_k4s2": [P, P, P, P, I, I, I, I, I, I, P],
         "cv_conv_transpose2d_k4s2": [P, P, P, P, I, I, I, I, I, I, P],
         "cv_im2col_k4s2_c3": [P, P, I, I, I, P],
@@ -61,7 +74,11 @@ def _declare(lib):
         "cv_cross_entropy_bwd": [P, L, P, P, P, P, P, L, I, I, P],
         "cv_gelu_bwd": [P, P, P, L, P],
         "cv_colsum_bf16": [P, L, P, P, I, I, P],
+        "cv_decode_step": [ctypes.POINTER(DecodeStepArgs), P],
+        "cv_sample_topk": [P, L, I, I, F, I, ctypes.POINTER(c_int), I, U64, P, P, P, P, L, P, P, P, P, P, P],
     })
+    lib.cv_decode_step_workspace_bytes.argtypes = [I, I]
+    lib.cv_decode_step_workspace_bytes.restype = L
     lib.cv_layernorm_bwd_workspace_bytes.argtypes = [I, I]
     lib.cv_layernorm_bwd_workspace_bytes.restype = L
     lib.cv_attn_bwd_workspace_bytes.argtypes = [I, I, I, I]

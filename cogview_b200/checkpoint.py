@@ -78,9 +78,18 @@ def load_checkpoint(model, optimizer=None, lr_scheduler=None, load_dir=None, *, 
     target = _unwrap(model)
     with torch.no_grad():
         target.load_state_dict(sd['module'], strict=strict)
+    if not release and not finetune and lr_scheduler is not None and no_load_optim and 'lr_scheduler' in sd:
+        lr_scheduler.load_state_dict(sd['lr_scheduler'])       # the schedule does not depend on the optimizer format
     if not release and not finetune and not no_load_optim:
         if optimizer is not None and 'optimizer' in sd:
-            optimizer.load_state_dict(sd['optimizer'])
+            try:
+                optimizer.load_state_dict(sd['optimizer'])
+            except (ValueError, KeyError, TypeError) as e:
+                # a reference checkpoint carries an FP16_Optimizer / DeepSpeed entry (utils.py:213-216), whose layout
+                # (fp32_from_fp16 groups, loss scaler) has no counterpart here: say so instead of failing obscurely
+                raise RuntimeError('checkpoint %s: the optimizer entry is not a state_dict of %s (%s); load it with '
+                                   'no_load_optim=True (weights, iteration and LR schedule are still restored)'
+                                   % (name, type(optimizer).__name__, e)) from e
         if lr_scheduler is not None and 'lr_scheduler' in sd:
             lr_scheduler.load_state_dict(sd['lr_scheduler'])
     if finetune or release:

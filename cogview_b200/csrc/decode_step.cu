@@ -1,0 +1,780 @@
+// One autoregressive decode step (one new token per sequence, all layers + logits) as ONE persistent kernel.
+//
+// Reference path: generation/sampling.py:147-151 calling GPT2Model.forward (model/gpt2_modeling.py:106-123) with one
+// token per sequence: per layer  LN1 -> QKV linear (mpu/layers.py:243) -> attention over the memory
+// (mpu/sparse_transformer.py:652-673) -> dense (mpu/layers.py:319) -> x + LN3 -> LN2 -> h->4h + GELU -> 4h->h ->
+// y + LN4 (mpu/sparse_transformer.py:314-342), then the final LayerNorm and the tied-embedding logits.
+//
+// The step is HBM bound: 7.86 GB of bf16 weights are read once per step.  Launching one small kernel
+// per linear leaves every launch in its ramp-up / drain (14 us for a 6 us-ideal launch, profiles/r01_*linear*), so:
+//
+//   * one CTA per SM, resident for the whole step (cooperative launch): 8 consumer warps + 1 producer warp;
+//   * every weight matrix is split into contiguous, byte-balanced row ranges, one per CTA (the 4h->h matrix as
+//     37 row ranges x 4 K quarters so that the activation operand of every matrix is [M, h]);
+//   * the producer warp walks the CTA's static schedule (all matrices of all layers, then the vocabulary matrix)
+//     and copies 16-row x KS-column slabs into a shared-memory ring with cp.async.bulk (one bulk copy per weight
+//     row segment, >= 512 B contiguous, L2 evict-first), completion on an mbarrier per stage.  Weights do not
+//     depend on activations, so the producer never waits for a grid barrier: while the consumers sit in one of the
+//     5 grid barriers of a layer (or in the attention phase) the ring fills with the next matrix and the HBM
+//     stream never stops;
+//   * consumer warps split K inside a stage, feed mma.sync.m16n8k16 (weights = A, 16 output columns as rows;
+//     activations = B, up to 8 sequences as columns) from shared memory with conflict-free 16-byte loads (row pitch
+//     = 64 mod 128 bytes; the k-permutation of the fragments is the same for A and B, so a dot product is unchanged),
+//     reduce the 8 partial tiles through shared memory and apply bias / GELU;
+//   * the Sandwich-LN glue (two abs-max LayerNorms + residual, mpu/sparse_transformer.py:40-44) is computed
+//     redundantly by every CTA straight into its shared-memory activation operand — no single-CTA kernels between
+//     the linears; the fp32 residual stream lives in two L2-resident buffers (owner CTAs write their slice);
+//   * attention over the K|V cache runs as (sequence, head, key-range) units, one per consumer warp; the last unit
+//     of a (sequence, head) to finish merges the partial softmax states (arrival counter), which avoids a sixth grid
+//     barrier; the new token's K/V are appended in place;
+//   * the K quarters of the 4h->h product are merged the same way (fixed summation order: deterministic).
+//
+// Everything exchanged between CTAs goes through L2 (ld.global.cg / st + fence + grid barrier): L1 is not coherent
+// and there is no kernel boundary to invalidate it.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/cogview_b200.h"
+
+namespace {
+using namespace cv;
+typedef __nv_bfloat16 bf16;
+
+constexpr int CW = 8;               // consumer warps
+constexpr int CT = CW * 32;         // consumer threads
+constexpr int NT = CT + 32;         // + one producer warp
+constexpr int TILE = 16;            // weight rows (output columns) per MMA tile
+constexpr int KG = 4;               // K groups of the 4h->h matrix
+constexpr int HD = 64;              // head dim
+constexpr int MAXST = 8;            // ring stages (upper bound)
+constexpr int NE = 5;               // bf16 pairs per thread and row in the glue: h <= 2 * CT * NE = 2560
+constexpr int MAXM = 8;
+constexpr int AUNR = 8;             // attention: 4-key groups in flight per warp iteration (32 keys)
+constexpr int PART_STRIDE = HD + 2; // attention partial: acc[64], m, l
+
+struct Params {
+    const cv_decode_layer* layers;
+    int L, h, heads, V, M, max_len;
+    float eps, eps_final;
+    const bf16 *wte, *wpe, *lnf_g, *lnf_b;
+    const int64_t *ids, *pos;
+    const int* cur_len;
+    bf16* cache;
+    int64_t cache_ls, cache_bs;
+    float* logits;
+    int64_t ldl;
+    // workspace
+    bf16 *qkv, *ctx, *attn_out, *h4, *mlp_out;
+    float *resid_a, *resid_b, *fc2_part, *attn_part;
+    unsigned int *attn_cnt, *fc2_cnt;
+    unsigned long long *bar_ctr, *bar_base;
+    int* err;
+    // derived on the host
+    int kstage, nst, stage_bytes, pitch, xpitch, S;
+    float scale_log2;
+};
+
+// shared-memory carve-up (bytes from the 1024-aligned base)
+constexpr int SM_BAR = 0;                                  // full[MAXST], empty[MAXST]
+constexpr int SM_FLAG = 2 * MAXST * 8;                     // int flags
+constexpr int SM_RED = 256;                                // float red[4][CW][MAXM + 1]
+constexpr int SM_PART = SM_RED + 4 * CW * (MAXM + 1) * 4;  // float part[2][CW][TILE][8]
+constexpr int SM_XOP = ((SM_PART + 2 * CW * TILE * 8 * 4) + 127) / 128 * 128;
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bflo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bfhi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
+    f[0] = bflo(u.x); f[1] = bfhi(u.x); f[2] = bflo(u.y); f[3] = bfhi(u.y);
+    f[4] = bflo(u.z); f[5] = bfhi(u.z); f[6] = bflo(u.w); f[7] = bfhi(u.w);
+}
+__device__ __forceinline__ uint32_t ldcg_u32(const void* p) { return __ldcg(reinterpret_cast<const unsigned int*>(p)); }
+__device__ __forceinline__ uint4 ldcg_u128(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+
+__device__ __noinline__ void step_fail(const Params& p, int code) {
+    if (p.err != nullptr) atomicExch(p.err, code);
+    printf("cogview_b200: decode_step_kernel wait timed out (code %d, block %d, thread %d)\n", code, blockIdx.x,
+           threadIdx.x);
+    __trap();
+}
+
+// a CTA's share of one weight matrix: rows [r0, r1) x columns [k0, k0 + h)
+struct Mat {
+    const bf16* W;
+    int64_t ldw;
+    int r0, r1, k0;
+};
+__device__ __forceinline__ Mat make_mat(const void* W, int64_t ldw, int N, int part, int nparts, int k0) {
+    Mat m;
+    m.W = static_cast<const bf16*>(W);
+    m.ldw = ldw;
+    m.r0 = (int)(((int64_t)N * part) / nparts);
+    m.r1 = (int)(((int64_t)N * (part + 1)) / nparts);
+    m.k0 = k0;
+    return m;
+}
+
+enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_F32 = 2 };
+
+template <int MR, int CPW>
+__global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int h = p.h, M = p.M;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    uint64_t* empty = full + MAXST;
+    int* flags = reinterpret_cast<int*>(smem + SM_FLAG);
+    float* red = reinterpret_cast<float*>(smem + SM_RED);
+    float* part = reinterpret_cast<float*>(smem + SM_PART);
+    const uint32_t xop = smem_u32(smem + SM_XOP);
+    const uint32_t ring = xop + ((MAXM * p.xpitch + 127) / 128) * 128;
+    const int nks = h / p.kstage;
+
+    if (tid == 0) {
+        for (int i = 0; i < p.nst; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], CW);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // ============================================================================================
+    // producer warp: the weight stream
+    // ============================================================================================
+    if (warp == CW) {
+        const uint64_t pol = evict_first_policy();
+        int st = 0;
+        uint32_t ph = 0;
+        auto produce = [&](const Mat& m) {
+            for (int r = m.r0; r < m.r1; r += TILE) {
+                const int rows = min(TILE, m.r1 - r);
+                for (int ks = 0; ks < nks; ++ks) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)(rows * p.kstage * 2));
+                    __syncwarp();
+                    if (lane < rows)
+                        bulk_g2s(ring + st * p.stage_bytes + lane * p.pitch,
+                                 m.W + (size_t)(r + lane) * m.ldw + m.k0 + ks * p.kstage, (uint32_t)(p.kstage * 2),
+                                 smem_u32(&full[st]), pol);
+                    if (++st == p.nst) { st = 0; ph ^= 1; }
+                }
+            }
+        };
+        for (int l = 0; l < p.L; ++l) {
+            const cv_decode_layer& Lw = p.layers[l];
+            produce(make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0));
+            produce(make_mat(Lw.w_dense, h, h, cta, G, 0));
+            produce(make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0));
+            produce(make_mat(Lw.w_fc2, 4 * (int64_t)h, h, cta / KG, G / KG, (cta % KG) * h));
+        }
+        produce(make_mat(p.wte, h, p.V, cta, G, 0));
+        return;
+    }
+
+    // ============================================================================================
+    // consumer warps
+    // ============================================================================================
+    const int g = lane >> 2, q = lane & 3;
+    const int kpw = p.kstage / CW;                 // k elements per warp and stage ( = 32 * CPW )
+    unsigned long long bar_target = *reinterpret_cast<volatile unsigned long long*>(p.bar_base);
+    const int t_cached = __ldg(p.cur_len);         // tokens cached before this step; the new token sits at index t
+    int st = 0, pbuf = 0;
+    uint32_t ph = 0;
+
+    // rows >= M of the activation operand stay zero for the whole kernel
+    for (int i = tid; i < MAXM * p.xpitch / 16; i += CT) sts128(xop + i * 16, make_uint4(0, 0, 0, 0));
+    named_bar_sync(1, CT);
+
+    auto grid_barrier = [&](int code) {
+        named_bar_sync(1, CT);
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(p.bar_ctr, 1ull);
+            bar_target += (unsigned long long)G;
+            unsigned long long v;
+            uint32_t spins = 0;
+            uint64_t t0 = 0;
+            while (true) {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.bar_ctr) : "memory");
+                if (v >= bar_target) break;
+                if ((++spins & 0xff) == 0) {
+                    const uint64_t now = global_timer_ns();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > CV_WAIT_TIMEOUT_NS) step_fail(p, code);
+                }
+            }
+        } else {
+            bar_target += (unsigned long long)G;
+        }
+        named_bar_sync(1, CT);
+    };
+
+    // y[m, n] for the CTA's rows of one matrix, x = the shared-memory operand
+    auto consume = [&](const Mat& m, int epi, const bf16* bias, void* out, int64_t ldo) {
+        for (int r = m.r0; r < m.r1; r += TILE) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int ks = 0; ks < nks; ++ks) {
+                mbar_wait(&full[st], ph);
+                const uint32_t wa = ring + st * p.stage_bytes + g * p.pitch + (warp * kpw + q * 8) * 2;
+                const uint32_t xa = xop + g * p.xpitch + (ks * p.kstage + warp * kpw + q * 8) * 2;
+                uint4 w0[CPW], w1[CPW], xv[CPW];
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) {
+                    w0[c] = lds128(wa + c * 64);
+                    w1[c] = lds128(wa + 8 * p.pitch + c * 64);
+                    xv[c] = lds128(xa + c * 64);
+                }
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) {
+                    mma_16816(d, w0[c].x, w1[c].x, w0[c].y, w1[c].y, xv[c].x, xv[c].y);
+                    mma_16816(d, w0[c].z, w1[c].z, w0[c].w, w1[c].w, xv[c].z, xv[c].w);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+                if (++st == p.nst) { st = 0; ph ^= 1; }
+            }
+            // D fragment: d0,d1 = (row g, cols 2q,2q+1), d2,d3 = (row g+8, ...); row = output column, col = sequence
+            float* pw = part + ((pbuf * CW + warp) * TILE) * 8;
+            pw[g * 8 + 2 * q] = d[0];
+            pw[g * 8 + 2 * q + 1] = d[1];
+            pw[(g + 8) * 8 + 2 * q] = d[2];
+            pw[(g + 8) * 8 + 2 * q + 1] = d[3];
+            named_bar_sync(1, CT);
+            if (tid < TILE * 8) {
+                const int mi = tid >> 4, nn = tid & 15;
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < CW; ++w) v += part[((pbuf * CW + w) * TILE + nn) * 8 + mi];
+                const int n = r + nn;
+                if (mi < M && n < m.r1) {
+                    if (epi == EPI_F32) {
+                        static_cast<float*>(out)[(size_t)mi * ldo + n] = v;
+                    } else {
+                        if (bias != nullptr) v += __bfloat162float(bias[n]);
+                        if (epi == EPI_BF16_GELU) v = gelu_tanh(v);
+                        static_cast<bf16*>(out)[(size_t)mi * ldo + n] = __float2bfloat16_rn(v);
+                    }
+                }
+            }
+            pbuf ^= 1;
+        }
+    };
+
+    // x operand <- M rows of h bf16 values written by other CTAs
+    auto load_x = [&](const bf16* src, int64_t ld, int koff) {
+        const int vpr = h / 8;
+        for (int i = tid; i < M * vpr; i += CT) {
+            const int mi = i / vpr, c = i - mi * vpr;
+            sts128(xop + mi * p.xpitch + c * 16, ldcg_u128(src + (size_t)mi * ld + koff + c * 8));
+        }
+        named_bar_sync(1, CT);
+    };
+
+    // Sandwich-LN glue, computed redundantly by every CTA:
+    //   v  = res + LN_post(gemm_out / (max|gemm_out| / 8))          (skipped when gemm_out == nullptr)
+    //   xn = LN_pre(v / (max|v| / 8))  -> shared-memory operand;   v -> res_out (this CTA's column slice only)
+    // res = res_in (fp32, L2) or, when res_in == nullptr, the embedding wte[ids] + wpe[pos].
+    auto glue = [&](const bf16* gemm_out, const bf16* g_post, const bf16* b_post, float eps_post, const float* res_in,
+                    float* res_out, const bf16* g_pre, const bf16* b_pre, float eps_pre) {
+        const float inv_h = 1.0f / h;
+        uint32_t gq[NE], bq[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int col = 2 * (tid + CT * e);
+            const bool ok = col < h;
+            gq[e] = ok ? __ldg(reinterpret_cast<const unsigned int*>(g_pre + col)) : 0u;
+            bq[e] = ok ? __ldg(reinterpret_cast<const unsigned int*>(b_pre + col)) : 0u;
+        }
+        auto residual = [&](int mi, int col) -> float2 {
+            if (res_in != nullptr) return __ldcg(reinterpret_cast<const float2*>(res_in + (size_t)mi * h + col));
+            const uint32_t a = __ldg(reinterpret_cast<const unsigned int*>(p.wte + (size_t)__ldg(p.ids + mi) * h + col));
+            const uint32_t b = __ldg(reinterpret_cast<const unsigned int*>(p.wpe + (size_t)__ldg(p.pos + mi) * h + col));
+            return make_float2(bflo(a) + bflo(b), bfhi(a) + bfhi(b));
+        };
+        // block-wide: s[m] <- sum over the row, mx <- max over everything; one named barrier
+        auto reduce = [&](float (&s)[MR], float& mx, int which) {
+#pragma unroll
+            for (int mi = 0; mi < MR; ++mi) s[mi] = warp_sum(s[mi]);
+            mx = warp_max(mx);
+            float* rw = red + (which * CW + warp) * (MAXM + 1);
+            if (lane == 0) {
+#pragma unroll
+                for (int mi = 0; mi < MR; ++mi) rw[mi] = s[mi];
+                rw[MAXM] = mx;
+            }
+            named_bar_sync(1, CT);
+#pragma unroll
+            for (int mi = 0; mi < MR; ++mi) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < CW; ++w) t += red[(which * CW + w) * (MAXM + 1) + mi];
+                s[mi] = t;
+            }
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < CW; ++w) t = fmaxf(t, red[(which * CW + w) * (MAXM + 1) + MAXM]);
+            mx = t;
+        };
+
+        float2 v[MR][NE];
+        if (gemm_out != nullptr) {
+            uint32_t gp[NE], bp[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int col = 2 * (tid + CT * e);
+                const bool ok = col < h;
+                gp[e] = ok ? __ldg(reinterpret_cast<const unsigned int*>(g_post + col)) : 0u;
+                bp[e] = ok ? __ldg(reinterpret_cast<const unsigned int*>(b_post + col)) : 0u;
+            }
+            float s[MR], amax = 0.f;
+#pragma unroll
+            for (int mi = 0; mi < MR; ++mi) {
+                s[mi] = 0.f;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int col = 2 * (tid + CT * e);
+                    const uint32_t u = (mi < M && col < h) ? ldcg_u32(gemm_out + (size_t)mi * h + col) : 0u;
+                    v[mi][e] = make_float2(bflo(u), bfhi(u));
+                    s[mi] += v[mi][e].x + v[mi][e].y;
+                    amax = fmaxf(amax, fmaxf(fabsf(v[mi][e].x), fabsf(v[mi][e].y)));
+                }
+            }
+            float2 rs[MR == 4 ? MR : 1][NE];      // small batches: fetch the residual under the first reduction
+            if (MR == 4) {
+#pragma unroll
+                for (int mi = 0; mi < MR; ++mi)
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        const int col = 2 * (tid + CT * e);
+                        rs[MR == 4 ? mi : 0][e] = (mi < M && col < h) ? residual(mi, col) : make_float2(0.f, 0.f);
+                    }
+            }
+            reduce(s, amax, 0);
+            const float c = amax * 0.125f;
+            float ss[MR], dummy = 0.f;
+#pragma unroll
+            for (int mi = 0; mi < MR; ++mi) {
+                const float mean = s[mi] * inv_h;
+                ss[mi] = 0.f;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    if (2 * (tid + CT * e) < h) {
+                        const float a = v[mi][e].x - mean, b = v[mi][e].y - mean;
+                        ss[mi] += a * a + b * b;
+                    }
+                }
+            }
+            reduce(ss, dummy, 1);
+#pragma unroll
+            for (int mi = 0; mi < MR; ++mi) {
+                const float mean = s[mi] * inv_h;
+                const float rstd = rsqrtf(ss[mi] * inv_h + eps_post * c * c);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int col = 2 * (tid + CT * e);
+                    float2 r;
+                    if (MR == 4) r = rs[MR == 4 ? mi : 0][e];
+                    else r = (mi < M && col < h) ? residual(mi, col) : make_float2(0.f, 0.f);
+                    v[mi][e].x = (v[mi][e].x - mean) * rstd * bflo(gp[e]) + bflo(bp[e]) + r.x;
+                    v[mi][e].y = (v[mi][e].y - mean) * rstd * bfhi(gp[e]) + bfhi(bp[e]) + r.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int mi = 0; mi < MR; ++mi)
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int col = 2 * (tid + CT * e);
+                    v[mi][e] = (mi < M && col < h) ? residual(mi, col) : make_float2(0.f, 0.f);
+                }
+        }
+        // residual stream out (owner slice), statistics of v
+        const int np = h / 2;
+        const int p_lo = (int)(((int64_t)np * cta) / G), p_hi = (int)(((int64_t)np * (cta + 1)) / G);
+        float s2[MR], amax2 = 0.f;
+#pragma unroll
+        for (int mi = 0; mi < MR; ++mi) {
+            s2[mi] = 0.f;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int pi = tid + CT * e;
+                if (mi < M && pi < np) {
+                    if (res_out != nullptr && pi >= p_lo && pi < p_hi)
+                        *reinterpret_cast<float2*>(res_out + (size_t)mi * h + 2 * pi) = v[mi][e];
+                    s2[mi] += v[mi][e].x + v[mi][e].y;
+                    amax2 = fmaxf(amax2, fmaxf(fabsf(v[mi][e].x), fabsf(v[mi][e].y)));
+                }
+            }
+        }
+        reduce(s2, amax2, 2);
+        const float c2 = amax2 * 0.125f;
+        float ss2[MR], dummy2 = 0.f;
+#pragma unroll
+        for (int mi = 0; mi < MR; ++mi) {
+            const float mean = s2[mi] * inv_h;
+            ss2[mi] = 0.f;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (mi < M && tid + CT * e < np) {
+                    const float a = v[mi][e].x - mean, b = v[mi][e].y - mean;
+                    ss2[mi] += a * a + b * b;
+                }
+            }
+        }
+        reduce(ss2, dummy2, 3);
+#pragma unroll
+        for (int mi = 0; mi < MR; ++mi) {
+            const float mean = s2[mi] * inv_h;
+            const float rstd = rsqrtf(ss2[mi] * inv_h + eps_pre * c2 * c2);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int pi = tid + CT * e;
+                if (mi < M && pi < np) {
+                    const float a = (v[mi][e].x - mean) * rstd * bflo(gq[e]) + bflo(bq[e]);
+                    const float b = (v[mi][e].y - mean) * rstd * bfhi(gq[e]) + bfhi(bq[e]);
+                    sts32(xop + mi * p.xpitch + pi * 4, pack_bf16x2(a, b));
+                }
+            }
+        }
+        named_bar_sync(1, CT);
+    };
+
+    // attention of the new token over keys 0..t (standard_attention for sq = 1), K|V cache of layer l
+    auto attention = [&](int l) {
+        bf16* cache_l = p.cache + (size_t)l * p.cache_ls;
+        const int grp = lane >> 3, sub = lane & 7;
+        const int t = t_cached, T = t + 1, S = p.S;
+        const int per = (T + S - 1) / S;
+        const int U = M * p.heads * S;
+        for (int u = cta + G * warp; u < U; u += G * CW) {
+            const int s = u % S, bh = u / S;
+            const int head = bh % p.heads, batch = bh / p.heads;
+            const bf16* qrow = p.qkv + (size_t)batch * 3 * h + head * HD + sub * 8;
+            float qf[8];
+            bf16x8_to_float(ldcg_u128(qrow), qf);
+            const uint4 knew = ldcg_u128(qrow + h);
+            const uint4 vnew = ldcg_u128(qrow + 2 * h);
+            bf16* kbase = cache_l + (size_t)batch * p.cache_bs + head * HD + sub * 8;
+            if (s == S - 1 && grp == 0 && t < p.max_len) {
+                *reinterpret_cast<uint4*>(kbase + (size_t)t * 2 * h) = knew;
+                *reinterpret_cast<uint4*>(kbase + (size_t)t * 2 * h + h) = vnew;
+            }
+            const int j0 = s * per, j1 = min(T, j0 + per);
+            float m = -INFINITY, lsum = 0.f, acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            for (int jb = j0; jb < j1; jb += 4 * AUNR) {
+                uint4 kr[AUNR], vr[AUNR];
+                bool valid[AUNR];
+#pragma unroll
+                for (int a = 0; a < AUNR; ++a) {
+                    const int j = jb + a * 4 + grp;
+                    valid[a] = j < j1;
+                    kr[a] = knew;
+                    vr[a] = vnew;
+                    if (valid[a] && j != t) {
+                        const bf16* kp = kbase + (size_t)j * 2 * h;
+                        kr[a] = __ldg(reinterpret_cast<const uint4*>(kp));
+                        vr[a] = __ldg(reinterpret_cast<const uint4*>(kp + h));
+                    }
+                }
+                float sc[AUNR];
+                float mn = m;
+#pragma unroll
+                for (int a = 0; a < AUNR; ++a) {
+                    float kf[8];
+                    bf16x8_to_float(kr[a], kf);
+                    float sdot = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sdot = fmaf(qf[i], kf[i], sdot);
+                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+                    sc[a] = valid[a] ? sdot * p.scale_log2 : -INFINITY;
+                    mn = fmaxf(mn, sc[a]);
+                }
+                if (mn > -INFINITY) {
+                    const float alpha = exp2f(m - mn);
+                    m = mn;
+                    lsum *= alpha;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] *= alpha;
+#pragma unroll
+                    for (int a = 0; a < AUNR; ++a) {
+                        const float pr = exp2f(sc[a] - mn);
+                        float vf[8];
+                        bf16x8_to_float(vr[a], vf);
+                        lsum += pr;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
+                    }
+                }
+            }
+            // merge the warp's four key groups (lanes with the same `sub`)
+#pragma unroll
+            for (int off = 8; off <= 16; off <<= 1) {
+                const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+                const float lo = __shfl_xor_sync(0xffffffffu, lsum, off);
+                const float mn = fmaxf(m, mo);
+                const float wa = (m == -INFINITY) ? 0.f : exp2f(m - mn);
+                const float wb = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+                lsum = lsum * wa + lo * wb;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float ao = __shfl_xor_sync(0xffffffffu, acc[i], off);
+                    acc[i] = acc[i] * wa + ao * wb;
+                }
+                m = mn;
+            }
+            float* dst = p.attn_part + (size_t)u * PART_STRIDE;
+            if (grp == 0) {
+                *reinterpret_cast<float2*>(dst + sub * 8) = make_float2(acc[0], acc[1]);
+                *reinterpret_cast<float2*>(dst + sub * 8 + 2) = make_float2(acc[2], acc[3]);
+                *reinterpret_cast<float2*>(dst + sub * 8 + 4) = make_float2(acc[4], acc[5]);
+                *reinterpret_cast<float2*>(dst + sub * 8 + 6) = make_float2(acc[6], acc[7]);
+                if (sub == 0) *reinterpret_cast<float2*>(dst + HD) = make_float2(m, lsum);
+            }
+            __threadfence();
+            __syncwarp();
+            unsigned int old = 0;
+            if (lane == 0) old = atomicAdd(p.attn_cnt + bh, 1u);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == (unsigned int)(S - 1)) {            // last unit of this (sequence, head): merge in split order
+                __threadfence();
+                const float* src = p.attn_part + (size_t)bh * S * PART_STRIDE;
+                float Mx = -INFINITY;
+                for (int s2 = 0; s2 < S; ++s2) Mx = fmaxf(Mx, __ldcg(src + s2 * PART_STRIDE + HD));
+                float Ls = 0.f, A0 = 0.f, A1 = 0.f;
+                for (int s2 = 0; s2 < S; ++s2) {
+                    const float ms = __ldcg(src + s2 * PART_STRIDE + HD);
+                    const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - Mx);
+                    Ls += __ldcg(src + s2 * PART_STRIDE + HD + 1) * w;
+                    A0 += __ldcg(src + s2 * PART_STRIDE + lane) * w;
+                    A1 += __ldcg(src + s2 * PART_STRIDE + 32 + lane) * w;
+                }
+                bf16* o = p.ctx + (size_t)batch * h + head * HD;
+                o[lane] = __float2bfloat16_rn(A0 / Ls);
+                o[lane + 32] = __float2bfloat16_rn(A1 / Ls);
+                if (lane == 0) p.attn_cnt[bh] = 0u;
+            }
+        }
+    };
+
+    // ------------------------------------------------------------------------------------------------
+    // the step
+    // ------------------------------------------------------------------------------------------------
+    const bf16* prev_post_g = nullptr;
+    const bf16* prev_post_b = nullptr;
+    for (int l = 0; l < p.L; ++l) {
+        const cv_decode_layer& Lw = p.layers[l];
+        // x = x_prev + LN4(mlp_out_prev)  (layer 0: the embedding);  xn = LN1(x)
+        glue(l == 0 ? nullptr : p.mlp_out, prev_post_g, prev_post_b, p.eps, l == 0 ? nullptr : p.resid_a, p.resid_b,
+             static_cast<const bf16*>(Lw.ln1_g), static_cast<const bf16*>(Lw.ln1_b), p.eps);
+        consume(make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0), EPI_BF16, static_cast<const bf16*>(Lw.b_qkv), p.qkv, 3 * h);
+        grid_barrier(100 + l);
+        attention(l);
+        grid_barrier(200 + l);
+        load_x(p.ctx, h, 0);
+        consume(make_mat(Lw.w_dense, h, h, cta, G, 0), EPI_BF16, static_cast<const bf16*>(Lw.b_dense), p.attn_out, h);
+        grid_barrier(300 + l);
+        // y = x + LN3(attn_out);  xn2 = LN2(y)
+        glue(p.attn_out, static_cast<const bf16*>(Lw.ln3_g), static_cast<const bf16*>(Lw.ln3_b), p.eps, p.resid_b,
+             p.resid_a, static_cast<const bf16*>(Lw.ln2_g), static_cast<const bf16*>(Lw.ln2_b), p.eps);
+        consume(make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0), EPI_BF16_GELU, static_cast<const bf16*>(Lw.b_fc1), p.h4, 4 * h);
+        grid_barrier(400 + l);
+        {
+            const int rg = cta / KG, kg = cta % KG;
+            load_x(p.h4, 4 * h, kg * h);
+            const Mat m2 = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, rg, G / KG, kg * h);
+            consume(m2, EPI_F32, nullptr, p.fc2_part + (size_t)kg * MAXM * h, h);
+            if (m2.r1 > m2.r0) {
+                __threadfence();
+                named_bar_sync(1, CT);
+                if (tid == 0) flags[0] = (atomicAdd(p.fc2_cnt + rg, 1u) == (unsigned int)(KG - 1)) ? 1 : 0;
+                named_bar_sync(1, CT);
+                if (flags[0]) {                          // last K quarter of this row range: sum in fixed order
+                    __threadfence();
+                    const int rows = m2.r1 - m2.r0;
+                    const bf16* b2 = static_cast<const bf16*>(Lw.b_fc2);
+                    for (int i = tid; i < M * rows; i += CT) {
+                        const int mi = i / rows, n = m2.r0 + (i - mi * rows);
+                        float v = 0.f;
+#pragma unroll
+                        for (int k2 = 0; k2 < KG; ++k2) v += __ldcg(p.fc2_part + ((size_t)k2 * MAXM + mi) * h + n);
+                        if (b2 != nullptr) v += __bfloat162float(b2[n]);
+                        p.mlp_out[(size_t)mi * h + n] = __float2bfloat16_rn(v);
+                    }
+                    if (tid == 0) p.fc2_cnt[rg] = 0u;
+                }
+            }
+        }
+        grid_barrier(500 + l);
+        prev_post_g = static_cast<const bf16*>(Lw.ln4_g);
+        prev_post_b = static_cast<const bf16*>(Lw.ln4_b);
+    }
+    // final: x = x + LN4(mlp_out);  logits = LN_f(x) wte^T
+    glue(p.mlp_out, prev_post_g, prev_post_b, p.eps, p.resid_a, nullptr, p.lnf_g, p.lnf_b, p.eps_final);
+    consume(make_mat(p.wte, h, p.V, cta, G, 0), EPI_F32, nullptr, p.logits, p.ldl);
+    if (cta == 0 && tid == 0) *p.bar_base = bar_target;
+}
+
+// workspace layout (bytes); the first WS_ZERO bytes hold counters and must start zeroed
+constexpr size_t WS_CTR = 0;        // bar_ctr u64, bar_base u64, err int
+constexpr size_t WS_FC2CNT = 64;    // u32[64]
+constexpr size_t WS_ATTNCNT = 320;  // u32[MAXM * heads]
+constexpr size_t WS_DATA = 8192;
+inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct WsLayout {
+    size_t qkv, ctx, attn_out, h4, mlp_out, resid_a, resid_b, fc2_part, attn_part, total;
+};
+WsLayout ws_layout(int h, int heads) {
+    WsLayout w;
+    size_t o = WS_DATA;
+    w.qkv = o; o += al256((size_t)MAXM * 3 * h * 2);
+    w.ctx = o; o += al256((size_t)MAXM * h * 2);
+    w.attn_out = o; o += al256((size_t)MAXM * h * 2);
+    w.h4 = o; o += al256((size_t)MAXM * 4 * h * 2);
+    w.mlp_out = o; o += al256((size_t)MAXM * h * 2);
+    w.resid_a = o; o += al256((size_t)MAXM * h * 4);
+    w.resid_b = o; o += al256((size_t)MAXM * h * 4);
+    w.fc2_part = o; o += al256((size_t)KG * MAXM * h * 4);
+    w.attn_part = o; o += al256((size_t)MAXM * heads * 16 * PART_STRIDE * 4);
+    w.total = o;
+    return w;
+}
+
+int step_grid() {
+    int g = cvh::num_sms();
+    return g - g % KG;
+}
+
+}  // namespace
+
+extern "C" int64_t cv_decode_step_workspace_bytes(int hidden, int heads) {
+    if (hidden <= 0 || heads <= 0) return -1;
+    return (int64_t)ws_layout(hidden, heads).total;
+}
+
+extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
+    CV_REQUIRE(a != nullptr && a->layers && a->wte && a->wpe && a->lnf_g && a->lnf_b && a->ids && a->pos &&
+                   a->cur_len && a->cache && a->logits && a->workspace,
+               "null pointer");
+    const int h = a->hidden, heads = a->heads, M = a->batch;
+    CV_REQUIRE(M >= 1 && M <= MAXM, "cv_decode_step handles 1 <= batch <= 8 sequences");
+    CV_REQUIRE(h > 0 && h % 256 == 0 && h <= 2 * CT * NE, "hidden must be a multiple of 256 and <= 2560");
+    CV_REQUIRE(heads > 0 && heads * HD == h && heads <= (1024 / MAXM), "hidden must be heads * 64");
+    CV_REQUIRE(a->num_layers >= 1 && a->vocab >= 1 && a->max_len >= 1 && a->ld_logits >= a->vocab, "bad sizes");
+    CV_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = step_grid();
+    CV_REQUIRE(grid >= KG && grid / KG <= 64, "unsupported SM count");
+
+    Params p;
+    p.layers = a->layers;
+    p.L = a->num_layers; p.h = h; p.heads = heads; p.V = a->vocab; p.M = M; p.max_len = a->max_len;
+    p.eps = a->eps; p.eps_final = a->eps_final;
+    p.wte = static_cast<const bf16*>(a->wte); p.wpe = static_cast<const bf16*>(a->wpe);
+    p.lnf_g = static_cast<const bf16*>(a->lnf_g); p.lnf_b = static_cast<const bf16*>(a->lnf_b);
+    p.ids = a->ids; p.pos = a->pos; p.cur_len = a->cur_len;
+    p.cache = static_cast<bf16*>(a->cache);
+    p.cache_ls = a->cache_layer_stride; p.cache_bs = a->cache_batch_stride;
+    p.logits = a->logits; p.ldl = a->ld_logits;
+    char* ws = static_cast<char*>(a->workspace);
+    const WsLayout w = ws_layout(h, heads);
+    p.bar_ctr = reinterpret_cast<unsigned long long*>(ws + WS_CTR);
+    p.bar_base = p.bar_ctr + 1;
+    p.err = reinterpret_cast<int*>(ws + WS_CTR + 16);
+    p.fc2_cnt = reinterpret_cast<unsigned int*>(ws + WS_FC2CNT);
+    p.attn_cnt = reinterpret_cast<unsigned int*>(ws + WS_ATTNCNT);
+    p.qkv = reinterpret_cast<bf16*>(ws + w.qkv); p.ctx = reinterpret_cast<bf16*>(ws + w.ctx);
+    p.attn_out = reinterpret_cast<bf16*>(ws + w.attn_out); p.h4 = reinterpret_cast<bf16*>(ws + w.h4);
+    p.mlp_out = reinterpret_cast<bf16*>(ws + w.mlp_out);
+    p.resid_a = reinterpret_cast<float*>(ws + w.resid_a); p.resid_b = reinterpret_cast<float*>(ws + w.resid_b);
+    p.fc2_part = reinterpret_cast<float*>(ws + w.fc2_part); p.attn_part = reinterpret_cast<float*>(ws + w.attn_part);
+
+    // stage = 16 weight rows x kstage columns; kstage = the largest multiple of 256 dividing h that is <= 1280
+    int kstage = 256;
+    for (int k = 256; k <= 1280; k += 256)
+        if (h % k == 0) kstage = k;
+    p.kstage = kstage;
+    p.pitch = kstage * 2 + 64;                       // 64 mod 128: conflict-free 16-byte fragment loads
+    p.xpitch = h * 2 + 64;
+    p.stage_bytes = TILE * p.pitch;
+    const int fixed = SM_XOP + ((MAXM * p.xpitch + 127) / 128) * 128;
+    int max_smem = 0, dev = 0;
+    CV_CUDA(cudaGetDevice(&dev));
+    CV_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int nst = (max_smem - fixed - 1024) / p.stage_bytes;
+    if (nst > MAXST) nst = MAXST;
+    CV_REQUIRE(nst >= 2, "not enough shared memory for the weight ring");
+    p.nst = nst;
+    const size_t smem_bytes = (size_t)fixed + (size_t)nst * p.stage_bytes;
+    int S = (grid * CW) / (M * heads);
+    S = S < 1 ? 1 : (S > 16 ? 16 : S);
+    p.S = S;
+    p.scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+
+    typedef void (*KernelFn)(const Params);
+    KernelFn fn = nullptr;
+    const int cpw = kstage / 256;
+#define DS_PICK(MR_)                                                    \
+    switch (cpw) {                                                      \
+        case 1: fn = decode_step_kernel<MR_, 1>; break;                 \
+        case 2: fn = decode_step_kernel<MR_, 2>; break;                 \
+        case 3: fn = decode_step_kernel<MR_, 3>; break;                 \
+        case 4: fn = decode_step_kernel<MR_, 4>; break;                 \
+        default: fn = decode_step_kernel<MR_, 5>; break;                \
+    }
+    if (M <= 4) { DS_PICK(4) } else { DS_PICK(8) }
+#undef DS_PICK
+    CV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    static int coop = -1;
+    if (coop < 0) {
+        const char* e = getenv("COGVIEW_B200_COOP");
+        int sup = 0;
+        cudaDeviceGetAttribute(&sup, cudaDevAttrCooperativeLaunch, dev);
+        coop = (sup && !(e && e[0] == '0')) ? 1 : 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = coop ? 1 : 0;
+    CV_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
+    cvh::count_launches(1);
+    return 0;
+}

@@ -88,13 +88,21 @@ sumsq_kernel(const __nv_bfloat16* __restrict__ x, size_t n, float* __restrict__ 
     }
 }
 
-// clip coefficient from the accumulated sum of squares: coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))
+// clip coefficient from the accumulated sum of squares: coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)).
+// A non-finite norm (one inf / NaN gradient anywhere) marks the step as skipped — the overflow branch of the
+// reference's FP16_Optimizer.step (fp16/fp16.py:399-420): state[0] = 1 and the applied-step counter state[1] is not
+// advanced; adamw_multi_kernel then leaves parameters, masters and moments untouched.
 __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef,
-                                 float* __restrict__ norm_out) {
+                                 float* __restrict__ norm_out, int* __restrict__ state) {
     const float nrm = sqrtf(*sumsq);
     if (norm_out) *norm_out = nrm;
+    const bool bad = !isfinite(nrm);
     const float c = max_norm / (nrm + 1e-6f);
-    *coef = (max_norm > 0.f && c < 1.f) ? c : 1.f;
+    *coef = bad ? 0.f : ((max_norm > 0.f && c < 1.f) ? c : 1.f);
+    if (state) {
+        state[0] = bad ? 1 : 0;
+        if (!bad) state[1] += 1;
+    }
 }
 
 // ---- multi-tensor variants: one launch for the whole parameter list (a 4B model has ~780 tensors, most of them
@@ -103,7 +111,8 @@ constexpr int MT_CTAS = 32;
 
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const cv_adamw_entry* __restrict__ table, float beta1, float beta2, float eps,
-                   const float* __restrict__ grad_scale_dev, float grad_scale) {
+                   const float* __restrict__ grad_scale_dev, float grad_scale, const int* __restrict__ state) {
+    if (state != nullptr && state[0] != 0) return;        // skipped step (non-finite gradient norm)
     const cv_adamw_entry e = table[blockIdx.y];
     const size_t n = (size_t)e.n, n4 = n / 4;
     if ((size_t)blockIdx.x * 256 >= n4 + 1) return;
@@ -111,7 +120,13 @@ adamw_multi_kernel(const cv_adamw_entry* __restrict__ table, float beta1, float 
     __nv_bfloat16* param = static_cast<__nv_bfloat16*>(e.param);
     const __nv_bfloat16* grad = static_cast<const __nv_bfloat16*>(e.grad);
     float *master = e.master, *m = e.m, *v = e.v;
-    const float lr = e.lr, weight_decay = e.weight_decay, bc1 = e.bias_correction1, bc2 = e.bias_correction2;
+    const float lr = e.lr, weight_decay = e.weight_decay;
+    float bc1 = e.bias_correction1, bc2 = e.bias_correction2;
+    if (state != nullptr) {                                // bias correction from the count of APPLIED steps
+        const float st = (float)state[1];
+        bc1 = 1.f - powf(beta1, st);
+        bc2 = 1.f - powf(beta2, st);
+    }
     for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
         uint2 gu = reinterpret_cast<const uint2*>(grad)[i];
         const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&gu);
@@ -214,18 +229,19 @@ extern "C" int cv_sumsq_bf16(const void* x, int64_t n, float* out, void* stream)
     return 0;
 }
 
-extern "C" int cv_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream) {
+extern "C" int cv_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, int* state,
+                            void* stream) {
     CV_REQUIRE(sumsq && coef, "null pointer");
-    clip_coef_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(sumsq, max_norm, coef, norm_out);
+    clip_coef_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(sumsq, max_norm, coef, norm_out, state);
     CV_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int cv_adamw_step_multi(const cv_adamw_entry* table_dev, int count, float beta1, float beta2, float eps,
-                                   const float* grad_scale_dev, float grad_scale, void* stream) {
+                                   const float* grad_scale_dev, float grad_scale, const int* state, void* stream) {
     CV_REQUIRE(table_dev && count > 0 && count <= 65535, "bad table");
     adamw_multi_kernel<<<dim3(MT_CTAS, count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        table_dev, beta1, beta2, eps, grad_scale_dev, grad_scale);
+        table_dev, beta1, beta2, eps, grad_scale_dev, grad_scale, state);
     CV_LAUNCH_CHECK();
     return 0;
 }

@@ -1,15 +1,27 @@
-"""Single-token decode step on the K|V cache, captured once as a CUDA graph and replayed per token.
+"""Single-token decode step on the K|V cache.
 
 This is the fast path behind GPT2Model.forward when it is called the way generation/sampling.py:147-151 calls
-it (one new token per sequence, `mems` returned by the previous call, mems_mode 'kv').  Per layer:
-abs-max LN -> QKV linear -> cached attention (+ append) -> out-proj (+abs-max) -> LN + residual -> LN ->
-h->4h (+GELU) -> 4h->h (+abs-max) -> LN + residual, all weight-streaming kernels (cv_linear_small_m,
-cv_attn_decode) with the position read from device memory so the graph is replayable."""
+it (one new token per sequence, `mems` returned by the previous call, mems_mode 'kv').
+
+Two device paths:
+  * batch <= 8 (default): the whole step — embedding, 48 Sandwich-LN layers, final LayerNorm, logits — is ONE
+    persistent kernel (cv_decode_step, csrc/decode_step.cu: TMA-staged weight stream in a shared-memory ring,
+    grid barriers between the dependency points), followed in generation runs by ONE sampling kernel
+    (cv_sample_topk).  Two kernels per generated token, captured as a CUDA graph.
+  * 9 <= batch <= 16, or COGVIEW_B200_PERSISTENT=0: one kernel per operation (cv_linear_small_m, cv_attn_decode,
+    cv_ln_pair_small_m), the round-1 path, also CUDA-graph captured.
+"""
+import os
+
 import torch
 import torch.nn.functional as F
 
 from .. import ops
 from .layers import _as_bf16
+
+
+def _persistent_enabled():
+    return os.environ.get('COGVIEW_B200_PERSISTENT', '1') != '0'
 
 
 class DecodeRunner:
@@ -24,33 +36,68 @@ class DecodeRunner:
         self.ids = torch.zeros((self.b, 1), dtype=torch.int64, device=dev)
         self.pos = torch.zeros((self.b, 1), dtype=torch.int64, device=dev)
         self.cur_len = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.logits = None
+        self.step_logits = None          # output buffer of the step (static: graphs write into it)
         self.graph = None
         self.use_graph = use_graph
+        self.persistent = (_persistent_enabled() and self.b <= ops.DECODE_STEP_MAX_BATCH and self.h % 256 == 0
+                           and self.h <= 2560)
         # enough (batch, head, split) CTAs to cover the SMs
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         # the key range of every (batch, head) is split so that ~8 CTAs per SM stream the K|V cache: the kernel is
         # latency-bound per CTA (4B, b=4: 160 (batch, head) pairs alone left it at ~0.7 us per 16 keys)
         self.nsplit = max(1, min(16, -(-8 * sms // (self.b * self.heads))))
         self.params = None
+        self.param_sig = None
         self.graph_launches = 0   # kernels per captured step
         self.replays = 0
+        self.last_t = -1
         # token-generation runs (model step + sampling in one graph, next token fed back on the device)
         self.sample_graphs = {}
         self.out_buf = torch.zeros((self.b, caches.maxlen + 1), dtype=torch.int64, device=dev)
         self.stepc = torch.zeros((1, 1), dtype=torch.int64, device=dev)
         self.score_acc = torch.zeros(self.b, dtype=torch.float32, device=dev)
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.done = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    # -- parameters --------------------------------------------------------------------------------------------
+    def _signature(self):
+        """(data_ptr, version) of every parameter the step reads: a load_state_dict / optimizer step / .to() after
+        the first generation must not leave the decode path on stale copies or stale pointers."""
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
 
     def _gather_params(self):
         tr = self.model.transformer
-        self.params = [tuple(_as_bf16(p.detach()) for p in layer.param_list()) for layer in tr.layers]
+        self.params = [tuple(_as_bf16(p.detach()).contiguous() for p in layer.param_list()) for layer in tr.layers]
         self.wte = _as_bf16(self.model.word_embeddings.weight.detach()).contiguous()
         self.wpe = _as_bf16(tr.position_embeddings.weight.detach()).contiguous()
-        self.fl = (_as_bf16(tr.final_layernorm.weight.detach()), _as_bf16(tr.final_layernorm.bias.detach()),
-                   tr.final_layernorm.eps)
+        self.fl = (_as_bf16(tr.final_layernorm.weight.detach()).contiguous(),
+                   _as_bf16(tr.final_layernorm.bias.detach()).contiguous(), tr.final_layernorm.eps)
         self.eps = tr.layers[0].layernorm_epsilon
+        self.param_sig = self._signature()
+        dev = self.ids.device
+        if self.persistent:
+            table = torch.tensor([[t.data_ptr() for t in P] for P in self.params], dtype=torch.int64)
+            self.layer_table = table.to(dev)
+            self.workspace = ops.decode_step_workspace(self.h, self.heads, dev)
+            self.step_logits = torch.empty((self.b, self.wte.shape[0]), dtype=torch.float32, device=dev)
+        # captured graphs hold the old pointers
+        self.graph = None
+        self.sample_graphs = {}
 
+    def _check_params(self):
+        if self.params is None or self.param_sig != self._signature():
+            self._gather_params()
+
+    # -- one step ----------------------------------------------------------------------------------------------
     def _run(self):
+        if self.persistent:
+            ops.decode_step(self.layer_table, len(self.params), self.heads, self.eps, self.fl[2], self.wte, self.wpe,
+                            self.fl[0], self.fl[1], self.ids, self.pos, self.cur_len, self.caches.buf,
+                            self.step_logits, self.workspace)
+            return self.step_logits
+        return self._run_per_op()
+
+    def _run_per_op(self):
         b, h, heads = self.b, self.h, self.heads
         L = len(self.params)
         scal = ops.new_scalars(2 * L + 1, self.ids.device)
@@ -74,12 +121,16 @@ class DecodeRunner:
             prev_am, prev_post = s[1:2], (g4, b4)
         _, xf = ops.ln_pair_small_m(x, prev_gemm, prev_am, prev_post, (self.fl[0], self.fl[1]), self.fl[2],
                                     want_res_out=False)
-        self.logits = ops.linear_small_m(xf, self.wte, out_dtype=torch.float32)
+        if self.step_logits is None:
+            self.step_logits = torch.empty((b, self.wte.shape[0]), dtype=torch.float32, device=self.ids.device)
+        return ops.linear_small_m(xf, self.wte, out=self.step_logits)
 
     def step(self, ids, pos, t):
-        """ids, pos: [b, 1] int64; t: tokens already cached.  Returns logits [b, V] fp32 (a static buffer)."""
-        if self.params is None:
-            self._gather_params()
+        """ids, pos: [b, 1] int64; t: tokens already cached.  Returns logits [b, V] fp32 (a static buffer that the
+        next step overwrites; the sampling graphs never modify it)."""
+        if self.params is None or t <= self.last_t:      # a new sequence: make sure the weights are the live ones
+            self._check_params()
+        self.last_t = t
         self.ids.copy_(ids)
         self.pos.copy_(pos)
         self.cur_len.fill_(t)
@@ -103,17 +154,25 @@ class DecodeRunner:
         else:
             self.graph.replay()
             self.replays += 1
-        return self.logits
+        return self.step_logits
 
     # -- generation runs: generation/sampling.py:147-183 with nothing left on the host per token -----------------
     def _sample_body(self, key):
         """One token: decode step, then the reference's sampling tail — temperature, invalid vocabulary slices,
-        top-k (generation/sampling.py:24-33 with the boolean index_put written as the equivalent masked_fill so that
-        it can be captured), softmax, torch.multinomial, beam log-probability — and the hand-over of the sampled
-        token to the next step, all through device-side state."""
+        top-k (generation/sampling.py:24-33), softmax, multinomial draw, beam log-probability — and the hand-over of
+        the sampled token to the next step, all through device-side state.  With the fused kernel the tail is ONE
+        launch (cv_sample_topk, own counter-based generator); COGVIEW_B200_FUSED_SAMPLING=0 keeps the reference's
+        torch operations (torch.multinomial's generator) instead."""
         temperature, top_k, inv = key
-        self._run()
-        logits = self.logits
+        logits = self._run()
+        vocab = logits.shape[1]
+        valid = ops.valid_ranges(inv, vocab)
+        if os.environ.get('COGVIEW_B200_FUSED_SAMPLING', '1') != '0' and 1 <= len(valid) <= 4:
+            ops.sample_topk(logits, temperature, top_k, valid, seed_dev=self.seed_dev, step=self.stepc,
+                            next_ids=self.ids, out_tokens=self.out_buf, score_acc=self.score_acc, pos=self.pos,
+                            cur_len=self.cur_len, done=self.done)
+            return
+        logits = logits.clone()
         logits.div_(temperature)
         for a, z in inv:
             logits[:, a:z] = -float('Inf')
@@ -139,12 +198,14 @@ class DecodeRunner:
     def sample_run(self, ids, pos, t, n_steps, temperature, top_k, invalid_slices):
         """n_steps tokens starting from `ids` ([b, 1], at positions `pos`, t tokens cached).  One graph replay per
         token.  Returns (tokens [b, n_steps] int64, summed log-probabilities [b] fp32)."""
-        if self.params is None:
-            self._gather_params()
+        self._check_params()
+        self.last_t = t + n_steps
         vocab = self.model.word_embeddings.weight.shape[0]
         key = (float(temperature), int(top_k), tuple(sl.indices(vocab)[:2] for sl in invalid_slices))
         assert n_steps <= self.out_buf.shape[1]
         self._reset_run(ids, pos, t)
+        # the draw generator of the fused tail: a fresh seed per run from torch's (seedable) host generator
+        self.seed_dev.copy_(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64), non_blocking=True)
         graph = self.sample_graphs.get(key)
         if graph is None and self.use_graph:
             dev = self.ids.device

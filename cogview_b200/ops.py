@@ -299,6 +299,78 @@ def ln_pair_small_m(res_in, gemm_out, absmax_gemm, post, pre, eps, *, want_res_o
     return y, xn
 
 
+DECODE_STEP_MAX_BATCH = 8
+
+
+def decode_step_workspace(hidden, heads, device):
+    """Zeroed workspace of the persistent decode step (counters + L2-resident activations)."""
+    n = lib().cv_decode_step_workspace_bytes(int(hidden), int(heads))
+    if n <= 0:
+        raise _lib.CogViewB200Error("cv_decode_step_workspace_bytes(%d, %d) failed" % (hidden, heads))
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def decode_step(layer_table, num_layers, heads, eps, eps_final, wte, wpe, lnf_g, lnf_b, ids, pos, cur_len, cache,
+                logits, workspace):
+    """One token per sequence through every layer + logits in ONE kernel (cv_decode_step).
+    layer_table: int64 [num_layers, 16] device tensor of parameter pointers in cv_decode_layer order;
+    cache: [L, b, max_len, 2h] bf16; ids/pos: int64 [b(,1)]; cur_len: int32 [1]; logits: fp32 [b, V] (written)."""
+    require_cuda(layer_table, wte, wpe, lnf_g, lnf_b, ids, pos, cur_len, cache, logits, workspace)
+    L, b, max_len, h2 = cache.shape
+    assert L == num_layers and cache.dtype == torch.bfloat16 and cache.stride(3) == 1 and cache.stride(2) == h2
+    assert layer_table.dtype == torch.int64 and layer_table.shape == (num_layers, 16) and layer_table.is_contiguous()
+    assert ids.dtype == torch.int64 and pos.dtype == torch.int64 and ids.numel() == b and pos.numel() == b
+    assert ids.is_contiguous() and pos.is_contiguous() and cur_len.dtype == torch.int32
+    assert logits.dtype == torch.float32 and logits.shape[0] == b and logits.stride(1) == 1
+    assert wte.dtype == torch.bfloat16 and wte.is_contiguous() and wpe.is_contiguous()
+    a = _lib.DecodeStepArgs(
+        layers=ptr(layer_table), num_layers=num_layers, hidden=h2 // 2, heads=heads, vocab=wte.shape[0], batch=b,
+        max_len=max_len, eps=float(eps), eps_final=float(eps_final), wte=ptr(wte), wpe=ptr(wpe), lnf_g=ptr(lnf_g),
+        lnf_b=ptr(lnf_b), ids=ptr(ids), pos=ptr(pos), cur_len=ptr(cur_len), cache=ptr(cache),
+        cache_layer_stride=cache.stride(0), cache_batch_stride=cache.stride(1), logits=ptr(logits),
+        ld_logits=logits.stride(0), workspace=ptr(workspace))
+    import ctypes
+    check(lib().cv_decode_step(ctypes.byref(a), stream_ptr()), "cv_decode_step")
+    return logits
+
+
+def valid_ranges(invalid, vocab):
+    """Complement of a list of [lo, hi) index pairs inside [0, vocab) as a sorted list of [lo, hi) pairs."""
+    inv = sorted((max(0, int(a)), min(vocab, int(z))) for a, z in invalid)
+    out, cur = [], 0
+    for a, z in inv:
+        if a > cur:
+            out.append((cur, a))
+        cur = max(cur, z)
+    if cur < vocab:
+        out.append((cur, vocab))
+    return out
+
+
+def sample_topk(logits, temperature, top_k, valid, *, seed=0, seed_dev=None, step=None, next_ids=None, out_tokens=None,
+                score_acc=None, pos=None, cur_len=None, done=None, want_probs=False):
+    """Sampling tail of generation/sampling.py:157-183 in one kernel.  logits fp32 [b, V] (unchanged);
+    valid: list of [lo, hi) vocabulary ranges (<= 4).  Returns (next_ids int64 [b], probs or None)."""
+    import ctypes
+    require_cuda(logits, seed_dev, step, next_ids, out_tokens, score_acc, pos, cur_len, done)
+    b, V = logits.shape
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1
+    if not 1 <= len(valid) <= 4:
+        raise _lib.CogViewB200Error("cv_sample_topk takes 1..4 valid vocabulary ranges, got %r" % (valid,))
+    if next_ids is None:
+        next_ids = torch.empty(b, dtype=torch.int64, device=logits.device)
+    if (step is not None or cur_len is not None) and done is None:
+        done = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    probs = torch.empty((b, logits.stride(0)), dtype=torch.float32, device=logits.device) if want_probs else None
+    flat = (ctypes.c_int * (2 * len(valid)))(*[int(x) for r in valid for x in r])
+    rc = lib().cv_sample_topk(ptr(logits), logits.stride(0), b, V, float(temperature), int(top_k), flat, len(valid),
+                              int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(seed_dev), ptr(step), ptr(next_ids), ptr(out_tokens),
+                              0 if out_tokens is None else out_tokens.stride(0), ptr(score_acc), ptr(pos), ptr(cur_len),
+                              ptr(done), ptr(probs), stream_ptr())
+    check(rc, "cv_sample_topk")
+    return next_ids, (probs[:, :V] if want_probs else None)
+
+
 # ----------------------------------------------------------------------------------------------------
 # VQ-VAE kernels (NHWC bf16 activations)
 # ----------------------------------------------------------------------------------------------------

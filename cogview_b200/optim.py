@@ -22,6 +22,51 @@ class FusedAdamW(torch.optim.Optimizer):
         self._copied = [None, None]  # CUDA event recorded after the async copy out of each staging buffer
         self._flip = 0
         self.last_grad_norm = None   # device tensor (1,) after step() when clipping is on
+        self._state = None           # device int32 [2]: [0] last step skipped (non-finite gradient norm), [1] applied steps
+        self._applied = 0            # applied steps restored from a checkpoint (seeds the device counter)
+
+    _FP32_STATE = ('master', 'exp_avg', 'exp_avg_sq')
+
+    @property
+    def last_step_skipped(self):
+        """Device int32 view (1,) — 1 when the last step() was skipped because the gradient norm was inf/NaN (the
+        overflow branch of FP16_Optimizer.step, fp16/fp16.py:399-420), or None before the first clipped step."""
+        return None if self._state is None else self._state[0:1]
+
+    def state_dict(self):
+        sd = super().state_dict()
+        if self._state is not None:
+            self._applied = int(self._state[1].item())
+        sd['applied_steps'] = self._applied
+        return sd
+
+    def load_state_dict(self, state_dict):
+        """torch.optim.Optimizer.load_state_dict casts every floating-point state tensor to the PARAMETER dtype (bf16
+        here), which would halve the fp32 masters and moments the kernels address as float*.  Restore them from the
+        incoming dict in fp32 after the generic load."""
+        state_dict = dict(state_dict)
+        self._applied = int(state_dict.pop('applied_steps', 0))
+        if 'state' not in state_dict or 'param_groups' not in state_dict or any(
+                'params' not in g for g in state_dict['param_groups']):
+            raise ValueError('FusedAdamW.load_state_dict: not a torch.optim state_dict (a reference FP16_Optimizer / '
+                             'DeepSpeed optimizer entry cannot be loaded: resume with no_load_optim)')
+        super().load_state_dict(state_dict)
+        saved_ids = [i for g in state_dict['param_groups'] for i in g['params']]
+        params = [p for g in self.param_groups for p in g['params']]
+        for idx, p in zip(saved_ids, params):
+            src = state_dict['state'].get(idx)
+            if src is None:
+                continue
+            st = self.state[p]
+            for k in self._FP32_STATE:
+                if k in src:
+                    st[k] = src[k].detach().to(device=p.device, dtype=torch.float32).contiguous().clone()
+            if 'step' in src:
+                st['step'] = int(src['step'])
+            if not self._applied:
+                self._applied = int(st.get('step', 0))
+        self._state = None
+        self._tables = None
 
     _ENTRY = np.dtype([('param', '<u8'), ('grad', '<u8'), ('master', '<u8'), ('m', '<u8'), ('v', '<u8'), ('n', '<i8'),
                        ('lr', '<f4'), ('wd', '<f4'), ('bc1', '<f4'), ('bc2', '<f4')])   # = cv_adamw_entry, 64 bytes
@@ -40,6 +85,10 @@ class FusedAdamW(torch.optim.Optimizer):
         rec = host.numpy().view(self._ENTRY)
         for i, (group, p) in enumerate(plist):
             st = self._state_for(p)
+            for k in self._FP32_STATE:
+                t = st[k]
+                assert t.dtype == torch.float32 and t.numel() == p.numel() and t.is_contiguous() and t.device == p.device, \
+                    "FusedAdamW state '%s' must be a contiguous fp32 tensor of the parameter's size" % k
             st['step'] += 1
             b1, b2 = group['betas']
             rec[i] = (p.data_ptr(), p.grad.data_ptr(), st['master'].data_ptr(), st['exp_avg'].data_ptr(),
@@ -81,12 +130,14 @@ class FusedAdamW(torch.optim.Optimizer):
         if self.max_grad_norm > 0:
             if self._scal is None or self._scal.device != dev:
                 self._scal = torch.zeros(3, dtype=torch.float32, device=dev)
+            if self._state is None or self._state.device != dev:
+                self._state = torch.tensor([0, self._applied], dtype=torch.int32, device=dev)
             self._scal.zero_()
             check(L.cv_sumsq_bf16_multi(ptr(table), len(plist), ptr(self._scal[0:1]), stream), "cv_sumsq_bf16_multi")
             check(L.cv_clip_coef(ptr(self._scal[0:1]), self.max_grad_norm, ptr(self._scal[1:2]), ptr(self._scal[2:3]),
-                                 stream), "cv_clip_coef")
+                                 ptr(self._state), stream), "cv_clip_coef")
             coef = self._scal[1:2]
             self.last_grad_norm = self._scal[2:3]
-        check(L.cv_adamw_step_multi(ptr(table), len(plist), float(b1), float(b2), float(eps), ptr(coef), 1.0, stream),
-              "cv_adamw_step_multi")
+        check(L.cv_adamw_step_multi(ptr(table), len(plist), float(b1), float(b2), float(eps), ptr(coef), 1.0,
+                                    ptr(self._state) if self.max_grad_norm > 0 else 0, stream), "cv_adamw_step_multi")
         return None

@@ -46,8 +46,10 @@ def forward_step(batch, model, txt_loss_scale=1.0, is_sparse=0, mems=()):
     return loss, mems, img_loss, txt_loss
 
 
-def train_step(batch, model, optimizer, lr_scheduler=None, txt_loss_scale=1.0, is_sparse=0, mems=()):
-    """pretrain_gpt2.py:406-450.  Returns (loss, skipped_iter, mems, img_loss, txt_loss)."""
+def train_step(batch, model, optimizer, lr_scheduler=None, txt_loss_scale=1.0, is_sparse=0, mems=(),
+               check_skipped=True):
+    """pretrain_gpt2.py:406-450.  Returns (loss, skipped_iter, mems, img_loss, txt_loss).  `check_skipped` reads the
+    optimizer's device-side skip flag (one small device->host read per step)."""
     lm_loss, mems, img_loss, txt_loss = forward_step(batch, model, txt_loss_scale, is_sparse, mems)
     partial = img_loss + txt_loss
     if partial.isnan().any() or partial.isinf().any():
@@ -56,6 +58,10 @@ def train_step(batch, model, optimizer, lr_scheduler=None, txt_loss_scale=1.0, i
     optimizer.zero_grad(set_to_none=True)
     lm_loss.backward()                    # torch DDP averages the gradients over the data-parallel group here
     optimizer.step()                      # FusedAdamW: global-norm clip + AdamW, no host sync
-    if lr_scheduler is not None:
+    # an inf / NaN gradient norm makes FusedAdamW leave every tensor untouched (fp16/fp16.py:399-420, the overflow
+    # branch of FP16_Optimizer.step): report it like the reference does and do not advance the schedule
+    flag = getattr(optimizer, 'last_step_skipped', None)
+    skipped = int(flag.item()) if (check_skipped and flag is not None) else 0
+    if lr_scheduler is not None and not skipped:
         lr_scheduler.step()
-    return lm_loss.detach(), 0, mems, img_loss, txt_loss
+    return lm_loss.detach(), skipped, mems, img_loss, txt_loss

@@ -169,6 +169,65 @@ int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_stride, con
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Whole decode step as ONE persistent kernel (1 <= batch <= 8): what GPT2Model.forward (model/gpt2_modeling.py:106-123)
+ * computes when generation/sampling.py:147-151 calls it with one new token per sequence — embedding, every
+ * Sandwich-LN layer (mpu/sparse_transformer.py:314-342: LN1, QKV, attention over the K|V cache + append, dense,
+ * x + LN3, LN2, h->4h + GELU, 4h->h, y + LN4), final LayerNorm and the tied-embedding logits.  One CTA per SM
+ * stays resident; a producer warp streams each CTA's share of every weight matrix through a shared-memory ring
+ * with cp.async.bulk (the stream runs ahead across the grid barriers of a layer), consumer warps feed mma.sync
+ * from shared memory; csrc/decode_step.cu has the design.
+ *   layers: DEVICE array of cv_decode_layer structs: bf16 tensors, reference parameter shapes, weights [out, in].
+ *   cache: [num_layers, batch, max_len, 2*hidden] bf16 (K | V), strides in elements; the new token is appended at
+ *     *cur_len.  ids / pos: int64 [batch].  logits: fp32 [batch, ld_logits].
+ *   workspace: cv_decode_step_workspace_bytes(hidden, heads) bytes, 256-byte aligned, ZEROED once by the caller
+ *     (it holds the grid-barrier and arrival counters, which the kernel leaves consistent for the next call).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cv_decode_layer {
+    const void *ln1_g, *ln1_b;       /* input_layernorm                       [h]      */
+    const void *w_qkv, *b_qkv;       /* attention.query_key_value             [3h, h]  */
+    const void *w_dense, *b_dense;   /* attention.dense                       [h, h]   */
+    const void *ln3_g, *ln3_b;       /* third_layernorm                                */
+    const void *ln2_g, *ln2_b;       /* post_attention_layernorm                       */
+    const void *w_fc1, *b_fc1;       /* mlp.dense_h_to_4h                     [4h, h]  */
+    const void *w_fc2, *b_fc2;       /* mlp.dense_4h_to_h                     [h, 4h]  */
+    const void *ln4_g, *ln4_b;       /* fourth_layernorm                               */
+} cv_decode_layer;                   /* 128 bytes */
+typedef struct cv_decode_step_args {
+    const cv_decode_layer* layers;
+    int num_layers, hidden, heads, vocab, batch, max_len;
+    float eps, eps_final;
+    const void *wte, *wpe, *lnf_g, *lnf_b;
+    const int64_t *ids, *pos;
+    const int* cur_len;
+    void* cache;
+    int64_t cache_layer_stride, cache_batch_stride;
+    float* logits;
+    int64_t ld_logits;
+    void* workspace;
+} cv_decode_step_args;               /* HOST struct */
+int64_t cv_decode_step_workspace_bytes(int hidden, int heads);
+int cv_decode_step(const cv_decode_step_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampling epilogue of the decode loop in one kernel (one CTA per sequence): generation/sampling.py:157-183 with
+ * top_k_logits (:24-33) — logits / temperature, invalid vocabulary slices, keep every logit >= the k-th largest
+ * (exact radix select; ties at the threshold are all kept, as `logits < kth` does), softmax over the kept ones,
+ * one multinomial draw (counter-based Philox: seed, draw index = *step, sequence), log-probability of the draw.
+ *   seed: *seed_dev when seed_dev != NULL (so that a captured graph can be re-seeded), else `seed`.
+ *   logits fp32 [b, ld] (not modified); valid: HOST array of n_valid (<= 4) [lo, hi) vocabulary ranges = the
+ *   complement of the reference's invalid_slices; top_k <= 0 keeps everything valid.
+ *   Outputs (all device, any may be NULL except next_ids): next_ids int64 [b] <- the draw; out_tokens int64
+ *   [b, ld_out] column *step <- the draw; score_acc fp32 [b] += log p(draw); pos int64 [b] += 1; cur_len int32 += 1;
+ *   step int64 += 1 (the shared scalars are advanced by the last CTA to finish); probs_out fp32 [b, ld] (testing):
+ *   the full post-filter distribution.
+ * ---------------------------------------------------------------------------------------------- */
+int cv_sample_topk(const float* logits, int64_t ld, int b, int vocab, float temperature, int top_k,
+                   const int* valid, int n_valid, uint64_t seed, const uint64_t* seed_dev, int64_t* step,
+                   int64_t* next_ids,
+                   int64_t* out_tokens, int64_t ld_out, float* score_acc, int64_t* pos, int* cur_len,
+                   unsigned int* done_counter, float* probs_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer step: fused AdamW on bf16 parameters with fp32 master weights / moments — replaces
  * FP16_Optimizer.step + apex FusedAdam (fp16/fp16.py:399-453, pretrain_gpt2.py:139-140; decoupled weight decay)
  * and, with cv_sumsq_bf16 + cv_clip_coef, the global-norm clipping of mpu/grads.py:28-74.
@@ -189,10 +248,15 @@ typedef struct cv_adamw_entry {
     int64_t n;
     float lr, weight_decay, bias_correction1, bias_correction2;
 } cv_adamw_entry;         /* 64 bytes */
+/* state (device int[2], may be NULL): [0] = 1 when this step is skipped, [1] = number of applied steps.
+ * cv_clip_coef sets state[0] = 1 (and coef = 0) when the gradient norm is inf/NaN — the overflow branch of
+ * FP16_Optimizer.step (fp16/fp16.py:399-420) — else state[0] = 0 and state[1] += 1; cv_adamw_step_multi with a
+ * non-NULL state leaves everything untouched on a skipped step and takes the bias corrections from state[1]
+ * instead of the table. */
 int cv_adamw_step_multi(const cv_adamw_entry* table_dev, int count, float beta1, float beta2, float eps,
-                        const float* grad_scale_dev, float grad_scale, void* stream);
+                        const float* grad_scale_dev, float grad_scale, const int* state, void* stream);
 int cv_sumsq_bf16_multi(const cv_adamw_entry* table_dev, int count, float* out, void* stream); /* over .grad/.n */
-int cv_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
+int cv_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, int* state, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * VQ-VAE image tokenizer (vqvae/vqvae_zc.py, vqvae/api.py), NHWC bf16 activations.

@@ -1,5 +1,6 @@
 """Checkpoint compatibility: the reference's directory layout, tracker file and dictionary keys
 (utils.py:158-166, :175-176, :188-232, :254-380; generate_samples.py:55-61; data_utils/vqvae_tokenizer.py:38-47)."""
+import math
 import os
 import random
 
@@ -120,3 +121,65 @@ def test_vqvae_checkpoint_with_dataparallel_prefix(tmp_path):
     ck.load_vqvae_checkpoint(dst, path)
     for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_fused_adamw_state_dict_round_trip_keeps_fp32_state(tmp_path):
+    """torch.optim.Optimizer.load_state_dict casts state tensors to the (bf16) parameter dtype; FusedAdamW must
+    restore master / exp_avg / exp_avg_sq as contiguous fp32 — the kernels address them as float* — bit for bit."""
+    from cogview_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(33).bfloat16()), torch.nn.Parameter(torch.randn(4, 8).bfloat16())]
+    opt = FusedAdamW([{'params': [ps[0]]}, {'params': [ps[1]], 'weight_decay': 0.0}], lr=1e-3, max_grad_norm=1.0)
+    for i, p in enumerate(ps):
+        st = opt._state_for(p)
+        st['step'] = 5
+        st['master'] += 1e-5 * (i + 1)          # not representable in bf16: a bf16 round trip would lose it
+        st['exp_avg'].normal_()
+        st['exp_avg_sq'].uniform_()
+    path = os.path.join(tmp_path, 'opt.pt')
+    torch.save(opt.state_dict(), path)
+    qs = [torch.nn.Parameter(torch.zeros(33).bfloat16()), torch.nn.Parameter(torch.zeros(4, 8).bfloat16())]
+    opt2 = FusedAdamW([{'params': [qs[0]]}, {'params': [qs[1]], 'weight_decay': 0.0}], lr=1e-3, max_grad_norm=1.0)
+    opt2.load_state_dict(torch.load(path, weights_only=False))
+    for p, q in zip(ps, qs):
+        a, b = opt.state[p], opt2.state[q]
+        assert b['step'] == 5
+        for k in ('master', 'exp_avg', 'exp_avg_sq'):
+            assert b[k].dtype == torch.float32 and b[k].is_contiguous() and torch.equal(a[k], b[k]), k
+    assert opt2._applied == 5
+    # a reference-format optimizer entry (FP16_Optimizer dict) is refused with a clear message
+    with pytest.raises(ValueError):
+        opt2.load_state_dict({'loss_scaler': None, 'optimizer_state_dict': {}, 'fp32_from_fp16': []})
+
+
+def test_annealing_lr_matches_reference_schedule_and_checkpoint_keys(tmp_path):
+    """learning_rates.py:22-88: warm-up + linear / cosine decay, and the state_dict keys a reference checkpoint holds."""
+    from cogview_b200 import checkpoint
+    from cogview_b200.learning_rates import AnnealingLR
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    opt = torch.optim.SGD(p, lr=1.0)
+    sch = AnnealingLR(opt, start_lr=4e-4, warmup_iter=10, num_iters=100, decay_style='cosine', last_iter=-1,
+                      decay_ratio=0.1)
+    assert opt.param_groups[0]['lr'] == 0.0
+    for _ in range(5):
+        sch.step()
+    assert abs(opt.param_groups[0]['lr'] - 4e-4 * 5 / 10) < 1e-12
+    for _ in range(55):
+        sch.step()
+    frac = (60 - 10) / 100
+    want = 4e-4 / 10 * ((math.cos(math.pi * frac) + 1) * (10 - 1) / 2 + 1)
+    assert abs(opt.param_groups[0]['lr'] - want) < 1e-12
+    sd = sch.state_dict()
+    assert set(sd) == {'warmup_iter', 'num_iters', 'decay_style', 'end_iter', 'decay_ratio'} and sd['num_iters'] == 60
+    # resume through load_checkpoint with a reference-style optimizer entry: no_load_optim keeps weights + schedule
+    model = torch.nn.Linear(2, 2)
+    name = checkpoint.get_checkpoint_name(str(tmp_path), 60)
+    os.makedirs(os.path.dirname(name), exist_ok=True)
+    torch.save({'iteration': 60, 'module': model.state_dict(), 'optimizer': {'loss_scaler': 1}, 'lr_scheduler': sd}, name)
+    open(checkpoint.get_checkpoint_tracker_filename(str(tmp_path)), 'w').write('60')
+    opt2 = torch.optim.SGD(model.parameters(), lr=1.0)
+    sch2 = AnnealingLR(opt2, 4e-4, 10, 100, 'cosine', -1, 0.1)
+    with pytest.raises(RuntimeError):
+        checkpoint.load_checkpoint(model, opt2, sch2, str(tmp_path))
+    it = checkpoint.load_checkpoint(model, opt2, sch2, str(tmp_path), no_load_optim=True)
+    assert it == 60 and sch2.num_iters == 60 and abs(opt2.param_groups[0]['lr'] - want) < 1e-12
