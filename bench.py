@@ -10,8 +10,10 @@ sequences, bf16, autoregressive sampling through the reference-facing API (gener
 over GPT2Model): one step = prefill a 65-token context and generate 1024 image tokens for a batch of 4 beams
 (scripts/text2image.sh defaults).  The same JSON line carries a `train` object for configs[2] (one optimizer
 step on 4 x 1088 tokens per GPU: forward, vocab cross-entropy, backward, DP gradient all-reduce, fused AdamW).
-Synthetic tokens, random-init weights (no network for checkpoints).  `--impl reference` times the oracle port
-of the reference's CPU path (hidden-state `mems` semantics) on the host cores.
+Synthetic tokens, random-init weights (no network for checkpoints).  `--impl reference` times the reference's
+own modules (oracle/_ref, placed by oracle/build_ref.py; hidden-state `mems` semantics) on the host cores — or the
+oracle port when oracle/_ref is absent.  The driver's record keeps only the contract keys of the JSON line, so the
+training / VQ-VAE results are also summarised inside `config` (`config.train`, `config.vqvae`).
 """
 import argparse
 import json
@@ -52,11 +54,13 @@ def parse():
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per launch from the committed ncu capture (profiles/r01_traffic.json), or None."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]["traffic_bytes_per_launch"]
-    except Exception:
-        return None
+    """DRAM bytes per launch from the committed ncu captures (profiles/r02_traffic.json, r01_traffic.json), or None."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]["traffic_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 def peaks():
@@ -235,46 +239,50 @@ def run_sample(args, cfg, world, rank, dev_index):
     return res
 
 
-def sample_roofline(model, nb, ms_per_step, gen_tokens):
-    """Dominant decode kernel = linear_small_m_kernel (weight streaming).  Algorithmic bytes per launch = the
-    bf16 weight matrix it reads (+ bias, x, y); timed live with CUDA events over one sweep of every layer's four
-    linears + the logits projection, i.e. the exact launch sequence of a decode step (7.9 GB >> the 126 MB L2,
-    so no weight is served from cache)."""
+def sample_roofline(model, nb, ms_per_step, gen_tokens, ctx_len=65):
+    """Dominant decode kernel = decode_step_kernel (one launch per token: all layers + logits, weight streaming).
+    Algorithmic bytes per launch: every bf16 weight once (7.858 GB) + the K|V rows of the cached
+    tokens (491,520 B x t per sequence).  Timed live with CUDA events over launches of the kernel alone at the mean
+    memory length of the generation (each launch streams 7.9 GB >> the 126 MB L2, so nothing is served from cache)."""
     from cogview_b200 import ops
+    from cogview_b200.mpu import kv_cache
+    from cogview_b200.mpu.decode import DecodeRunner
     pk = peaks()
     tr = model.transformer
-    h = tr.hidden_size
-    mats = []
-    for layer in tr.layers:
-        P = layer.param_list()
-        mats += [(P[2], P[3]), (P[4], P[5]), (P[10], P[11]), (P[12], P[13])]
-    mats.append((model.word_embeddings.weight, None))
-    xs = {h: torch.randn((nb, h), device="cuda").to(torch.bfloat16),
-          4 * h: torch.randn((nb, 4 * h), device="cuda").to(torch.bfloat16)}
-
-    def sweep():
-        for w, b in mats:
-            ops.linear_small_m(xs[w.shape[1]], w.detach(), None if b is None else b.detach())
-    for _ in range(2):
-        sweep()
+    c = kv_cache._Caches(tr, nb, torch.device("cuda"))
+    c.buf.normal_()
+    t_mean = ctx_len + gen_tokens // 2
+    c.t = t_mean
+    r = DecodeRunner(model, c, use_graph=False)
+    if not r.persistent:
+        return dict(kernel="linear_small_m_kernel", bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None,
+                    traffic=None, note="batch > 8: per-operation decode path, not measured here")
+    r._check_params()
+    r.ids.fill_(7)
+    r.pos.fill_(t_mean)
+    r.cur_len.fill_(t_mean)
+    for _ in range(3):
+        r._run()
     torch.cuda.synchronize()
+    reps = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
     e0.record()
     for _ in range(reps):
-        sweep()
+        r._run()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    nbytes = sum(w.numel() * 2 + (0 if b is None else b.numel() * 2) + nb * (w.shape[0] + w.shape[1]) * 2
-                 for w, b in mats)
+    wbytes = sum(p.numel() * 2 for p in model.parameters())
+    kvbytes = len(tr.layers) * nb * t_mean * 2 * tr.hidden_size * 2
+    nbytes = wbytes + kvbytes
     achieved = nbytes / (ms / 1e3) / 1e9
-    return dict(kernel="linear_small_m_kernel", bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s",
-                frac=achieved / pk["hbm"], traffic=measured_traffic("linear_small_m_kernel"),
-                traffic_note="ncu capture of the four per-layer shapes (profiles/r01_traffic.json): 1.001x algorithmic",
-                peak_source=pk["src"], launches_per_step=len(mats),
-                bytes_per_launch=nbytes / len(mats), avg_launch_us=ms * 1e3 / len(mats),
-                share_of_step=ms / (ms_per_step / gen_tokens), note="share_of_step = linear sweep / one decode step")
+    del r, c
+    return dict(kernel="decode_step_kernel", bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s",
+                frac=achieved / pk["hbm"], traffic=measured_traffic("decode_step_kernel"), peak_source=pk["src"],
+                launches_per_step=gen_tokens, bytes_per_launch=nbytes, avg_launch_us=ms * 1e3,
+                share_of_step=ms * gen_tokens / ms_per_step,
+                note="bytes = all weights + K|V of t=%d cached tokens x %d seqs; share_of_step = kernel x tokens / step" % (
+                    t_mean, nb))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -392,8 +400,7 @@ def gemm_roofline(cfg, M):
 # VQ-VAE tokenizer workload (configs[3]): encode + quantise + decode of 256x256 images
 # ----------------------------------------------------------------------------------------------------
 def run_vqvae(args, world, rank, dev_index, steps, warmup):
-    from cogview_b200 import vqvae
-    from oracle import recipes
+    from cogview_b200 import recipes, vqvae
     model = vqvae.new_model()
     model.load_state_dict(recipes.vqvae_state_dict(seed=0))
     model = model.cuda().eval()
@@ -494,6 +501,23 @@ def best_cpu_threads():
 
 
 def cpu_baseline_vqvae(nimg=4):
+    if reference_available() and os.environ.get("COGVIEW_B200_CPU_ARM", "reference") != "port":
+        from cogview_b200 import recipes
+        from oracle import ref_harness
+        R = ref_harness.load()
+        cores = best_cpu_threads()
+        model = R["vq_api"].new_model()
+        model.load_state_dict(recipes.vqvae_state_dict(seed=0))
+        model.eval()
+        img = recipes.images(nimg, size=256, seed=1)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            codes = R["vq_api"].img2code(model, img)
+            R["vq_api"].code2img(model, codes.view(nimg, 32, 32))
+            dt = time.perf_counter() - t0
+        return dict(value=nimg / dt, unit="images/s", cores=cores, kind="reference",
+                    sample="reference vqvae.api (unmodified, oracle/_ref), fp32, %d threads: img2code + code2img of %d "
+                           "256x256 images (%.1f s)" % (cores, nimg, dt))
     from oracle import cogview_oracle as O
     from oracle import recipes
     cores = best_cpu_threads()
@@ -510,7 +534,76 @@ def cpu_baseline_vqvae(nimg=4):
 # ----------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference path on the host cores
 # ----------------------------------------------------------------------------------------------------
+def reference_available():
+    try:
+        from oracle import ref_harness
+        return ref_harness.available()
+    except Exception:
+        return False
+
+
+def cpu_reference_sample(cfg, nb, gen_tokens, budget_s=20.0):
+    """The reference's OWN modules (oracle/_ref or /root/reference: model/gpt2_modeling.py GPT2Model over
+    mpu/sparse_transformer.py, unmodified, under the four harness shims) on the host cores, fp32: the decode call of
+    generation/sampling.py:147-151 — one new token per beam, hidden-state `mems` of length t, so the whole memory is
+    re-normalised and re-projected every step (mpu/sparse_transformer.py:320,136-141).  Bounded sample: a
+    2-layer 4B-width model (embedding + logits included) timed at a few memory lengths; per-layer cost fitted
+    linearly in t and integrated over the generated positions x 48 layers + the per-step head cost."""
+    from oracle import ref_harness
+    R = ref_harness.load()
+    cores = best_cpu_threads()
+    NL = 2
+    h, heads, V = cfg["hidden_size"], cfg["num_attention_heads"], cfg["vocab_size"]
+    t_start = time.perf_counter()
+    torch.manual_seed(0)
+    model = R["gpt2_modeling"].GPT2Model(
+        num_layers=NL, vocab_size=V, hidden_size=h, num_attention_heads=heads, embedding_dropout_prob=0.0,
+        attention_dropout_prob=0.0, output_dropout_prob=0.0, max_sequence_length=cfg["max_sequence_length"],
+        max_memory_length=cfg["max_sequence_length"], checkpoint_activations=False).eval()
+    pts = []
+    with torch.no_grad():
+        tok = torch.randint(0, 8192, (nb, 1))
+        # head cost: embedding + final LayerNorm + logits GEMM of one token (a 0-layer pass is not constructible)
+        x = torch.randn((nb, 1, h))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.linear(model.transformer.final_layernorm(x), model.word_embeddings.weight)
+        head_s = (time.perf_counter() - t0) / 3
+        for t in (64, 576, 1088):
+            mems = [torch.randn((nb, t, h)) for _ in range(NL + 1)]
+            pos = torch.full((nb, 1), t, dtype=torch.long)
+            model(tok, pos, 0, None, None, 0, *mems)                       # warm-up
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 2 or (time.perf_counter() - t0 < 2.0 and reps < 50):
+                model(tok, pos, 0, None, None, 0, *mems)
+                reps += 1
+            pts.append((t, (time.perf_counter() - t0) / reps))
+            if time.perf_counter() - t_start > budget_s:
+                break
+    per_layer = [(t, max(0.0, c - head_s) / NL) for t, c in pts]
+    n = len(per_layer)
+    mt, mc = sum(q[0] for q in per_layer) / n, sum(q[1] for q in per_layer) / n
+    bcoef = (sum((q[0] - mt) * (q[1] - mc) for q in per_layer) / max(1e-12, sum((q[0] - mt) ** 2 for q in per_layer))
+             if n > 1 else 0.0)
+    acoef = mc - bcoef * mt
+    ctx = 65
+    total = sum(cfg["num_layers"] * (acoef + bcoef * t) + head_s for t in range(ctx, ctx + gen_tokens))
+    wall = time.perf_counter() - t_start
+    return dict(value=nb * gen_tokens / total, unit="tokens/s", cores=cores, kind="reference", sample_wall_s=wall,
+                sample="reference GPT2Model (unmodified, oracle/_ref), fp32, %d threads: %d-layer 4B-width model, one decode "
+                       "call per memory length %s (batch %d, hidden-state mems); per-layer cost fitted linearly, x %d "
+                       "layers + head, integrated over %d positions (= %.0f s per full step); %.1f s of CPU work" % (
+                           cores, NL, [q[0] for q in pts], nb, cfg["num_layers"], gen_tokens, total, wall))
+
+
 def cpu_baseline_sample(cfg, nb, gen_tokens, budget_s=20.0):
+    if reference_available() and os.environ.get("COGVIEW_B200_CPU_ARM", "reference") != "port":
+        return cpu_reference_sample(cfg, nb, gen_tokens, budget_s)
+    return cpu_port_sample(cfg, nb, gen_tokens, budget_s)
+
+
+def cpu_port_sample(cfg, nb, gen_tokens, budget_s=20.0):
     """Reference semantics (generation/sampling.py:147-151 over mpu/sparse_transformer.py:320,136-141): each step
     re-normalises and re-projects the whole hidden-state memory.  Sample: ONE 4B-shaped layer (fp32) timed at a
     few memory lengths with batch nb, cost fitted linearly in the memory length and integrated over the
@@ -559,7 +652,44 @@ def cpu_baseline_sample(cfg, nb, gen_tokens, budget_s=20.0):
                            time.perf_counter() - t_start))
 
 
+def cpu_reference_train(cfg):
+    """The reference's GPT2Model (1 layer, 4B width) + mpu.vocab_parallel_cross_entropy, forward + backward at b=1,
+    s=1088, fp32 on the host cores; per-layer cost = total - head (embedding, logits GEMM, cross-entropy), x 48."""
+    from oracle import ref_harness
+    R = ref_harness.load()
+    cores = best_cpu_threads()
+    s_len = cfg["max_sequence_length"] - 1
+    h, V = cfg["hidden_size"], cfg["vocab_size"]
+    torch.manual_seed(0)
+    model = R["gpt2_modeling"].GPT2Model(
+        num_layers=1, vocab_size=V, hidden_size=h, num_attention_heads=cfg["num_attention_heads"],
+        embedding_dropout_prob=0.0, attention_dropout_prob=0.0, output_dropout_prob=0.0,
+        max_sequence_length=cfg["max_sequence_length"], max_memory_length=0, checkpoint_activations=False).train()
+    tok = torch.randint(0, V, (1, s_len))
+    lab = torch.randint(0, V, (1, s_len))
+    pos = torch.arange(s_len).unsqueeze(0)
+    mask = torch.tril(torch.ones((1, 1, s_len, s_len)))
+    t0 = time.perf_counter()
+    logits, *_ = model(tok, pos, mask, None, None, 0)
+    R["mpu"].vocab_parallel_cross_entropy(logits.contiguous().float(), lab).mean().backward()
+    full_s = time.perf_counter() - t0
+    hid = torch.randn((1, s_len, h), requires_grad=True)
+    w = model.word_embeddings.weight
+    t0 = time.perf_counter()
+    lg = torch.nn.functional.linear(hid, w)
+    R["mpu"].vocab_parallel_cross_entropy(lg.contiguous().float(), lab).mean().backward()
+    head_s = time.perf_counter() - t0
+    layer_s = max(1e-6, full_s - head_s)
+    total = cfg["num_layers"] * layer_s + head_s
+    return dict(value=s_len / total, unit="tokens/s", cores=cores, kind="reference",
+                sample="reference GPT2Model (unmodified, oracle/_ref), fp32, %d threads: 1-layer 4B-width fwd+bwd at b=1, "
+                       "s=%d (%.1f s, of which head %.1f s) -> x %d layers + head; extrapolated, optimizer not included" % (
+                           cores, s_len, full_s, head_s, cfg["num_layers"]))
+
+
 def cpu_baseline_train(cfg, budget_s=25.0):
+    if reference_available() and os.environ.get("COGVIEW_B200_CPU_ARM", "reference") != "port":
+        return cpu_reference_train(cfg)
     from oracle import cogview_oracle as O
     from oracle import recipes
     cores = best_cpu_threads()
@@ -587,6 +717,10 @@ def cpu_baseline_train(cfg, budget_s=25.0):
 
 
 # ----------------------------------------------------------------------------------------------------
+def _compact(d, keys):
+    return {k: d[k] for k in keys if k in d}
+
+
 def main():
     args = parse()
     cfg = MODEL_4B if args.model == "4b" else MODEL_TINY
@@ -594,34 +728,44 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload_name = ("configs[1]: CogView-base 4B (48L, d=2560, 40H, V=58240), seq 1089, bf16, AR sampling: prefill 65 "
-                     "+ generate %d tokens, %d beams/GPU, top-k 200, KV cache + CUDA-graph decode" % (
-                         args.gen_tokens, args.batch))
-    base = dict(metric="tokens/sec (AR sample; train in `train`) CogView-4B seq1089", unit="tokens/s", n_gpus=world,
-                steps=args.steps, warmup=args.warmup, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="bf16", data="synthetic tokens, random-init weights")
+                     "+ generate %d tokens, %d beams/GPU, top-k 200; persistent one-kernel decode step + fused "
+                     "sampling kernel (CUDA graph)" % (args.gen_tokens, args.batch))
+    # BASELINE.json's metric; `value` is the AR-sampling tokens/s (configs[1]), the training step (configs[2]) and the
+    # VQ-VAE round trip (configs[3]) are summarised in config.train / config.vqvae and in full in `train` / `vqvae`
+    base = dict(metric="tokens/sec (train + AR sample) CogView-4B seq1089 @1/2/4/8 B200; %roofline", unit="tokens/s",
+                n_gpus=world, steps=args.steps, warmup=args.warmup, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="bf16", data="synthetic tokens, random-init weights")
 
     if args.impl == "reference":
+        # The reference's own CPU path on this box's host cores.  A "step" here is one bounded sample of the workload
+        # (see cpu_reference_sample); ms_per_step is the sample's real duration, value the throughput it implies.
         if rank != 0:
             return
         t0 = time.perf_counter()
-        vals = []
-        for _ in range(max(1, min(args.steps, 2))):
+        vals, walls = [], []
+        for _ in range(args.warmup and 1):
+            cpu_baseline_sample(cfg, args.batch, args.gen_tokens, budget_s=8.0)
+        for _ in range(max(1, min(args.steps, 3))):
+            ts = time.perf_counter()
             cb = cpu_baseline_sample(cfg, args.batch, args.gen_tokens, budget_s=15.0)
+            walls.append(time.perf_counter() - ts)
             vals.append(cb["value"])
         cb["value"] = statistics.median(vals)
-        line = dict(base, impl="reference", value=cb["value"], ms_per_step=args.batch * args.gen_tokens / cb["value"] * 1e3,
-                    dtype="f32", cpu_baseline=cb, config=dict(workload=workload_name, parallelism="cpu"),
+        line = dict(base, impl="reference", value=cb["value"], ms_per_step=statistics.median(walls) * 1e3,
+                    steps=len(vals), dtype="f32", cpu_baseline=cb,
+                    config=dict(workload=workload_name, global_batch=args.batch, seq_len=1089, parallelism="cpu",
+                                note="each step = one bounded sample of the workload on the host cores"),
                     e2e=dict(value=cb["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0, wall_s=time.perf_counter() - t0)
         if args.workload in ("train", "both", "all"):
-            line["train"] = dict(cpu_baseline=cpu_baseline_train(cfg))
-            line["train"]["value"] = line["train"]["cpu_baseline"]["value"]
+            tb = cpu_baseline_train(cfg)
+            line["config"]["train"] = dict(value=tb["value"], unit="tokens/s", kind=tb["kind"], cores=tb["cores"])
         print(json.dumps(line))
         return
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback (use --impl reference for the "
-                         "CPU oracle)")
+                         "CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -643,6 +787,9 @@ def main():
             line.update(metric="images/sec (VQ-VAE encode+quantise+decode, 256x256)", unit="images/s", value=v["value"],
                         ms_per_step=v["ms_per_step"], e2e=v["e2e"], clocks=v["clocks"], gpu_launches=v["gpu_launches"],
                         roofline=v["roofline_step"], config=v["config"], steps=v["steps"], warmup=v["warmup"])
+        else:
+            line["config"]["vqvae"] = dict(value=v["value"], unit="images/s", ms_per_step=v["ms_per_step"],
+                                           frac_of_sustained_tensor_peak=v["roofline_step"]["frac"])
         line["vqvae"] = v
     if args.workload in ("train", "both", "all"):
         tsteps = args.train_steps or max(3, args.steps)
@@ -651,6 +798,14 @@ def main():
             line.update(metric="tokens/sec (train) CogView-4B seq1089", value=t["value"], ms_per_step=t["ms_per_step"],
                         e2e=t["e2e"], clocks=t["clocks"], gpu_launches=t["gpu_launches"], roofline=t["roofline"],
                         config=t["config"], steps=t["steps"], warmup=t["warmup"])
+        else:
+            # configs[2] — the workload with the one collective of the path (bf16 gradient all-reduce): kept inside
+            # `config` so that the per-N records of a scaling run carry it
+            line["config"]["train"] = dict(value=t["value"], unit="tokens/s", ms_per_step=t["ms_per_step"],
+                                           global_batch=t["config"]["global_batch"], e2e=t["e2e"]["value"],
+                                           step_frac_of_sustained_tensor_peak=t["roofline_step"]["frac"],
+                                           gemm_frac_of_burst_peak=t["roofline"]["frac"], loss=t["loss"],
+                                           exposed_comm_ms=t.get("exposed_comm_ms"))
         line["train"] = t
     if rank == 0 and args.skip_cpu_baseline:        # development runs only: the contract line carries cpu_baseline
         line["cpu_baseline"] = None

@@ -32,7 +32,7 @@ class DecodeStepArgs(ctypes.Structure):
                 ("ids", c_void_p), ("pos", c_void_p), ("cur_len", c_void_p),
                 ("cache", c_void_p), ("cache_layer_stride", c_int64), ("cache_batch_stride", c_int64),
                 ("logits", c_void_p), ("ld_logits", c_int64),
-                ("workspace", c_void_p)]
+                ("workspace", c_void_p), ("prof", c_void_p)]
 
 
 def _declare(lib):
@@ -74,9 +74,15 @@ def _declare(lib):
         "cv_cross_entropy_bwd": [P, L, P, P, P, P, P, L, I, I, P],
         "cv_gelu_bwd": [P, P, P, L, P],
         "cv_colsum_bf16": [P, L, P, P, I, I, P],
+        "cv_attn_sparse_fwd": [P, L, L, P, L, L, P, L, L, P, P, L, L, P, P, I, I, I, I, I, I, I, P],
+        "cv_attn_sparse_bwd": [P, L, L, P, L, L, P, L, L, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
         "cv_decode_step": [ctypes.POINTER(DecodeStepArgs), P],
         "cv_sample_topk": [P, L, I, I, F, I, ctypes.POINTER(c_int), I, U64, P, P, P, P, L, P, P, P, P, P, P],
     })
+    lib.cv_attn_sparse_workspace_bytes.argtypes = [I, I, I, I]
+    lib.cv_attn_sparse_workspace_bytes.restype = L
+    lib.cv_attn_sparse_bwd_workspace_bytes.argtypes = [I, I, I, I, I]
+    lib.cv_attn_sparse_bwd_workspace_bytes.restype = L
     lib.cv_decode_step_workspace_bytes.argtypes = [I, I]
     lib.cv_decode_step_workspace_bytes.restype = L
     lib.cv_layernorm_bwd_workspace_bytes.argtypes = [I, I]

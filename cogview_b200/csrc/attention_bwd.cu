@@ -29,7 +29,8 @@ constexpr int TILE_BYTES = BLK * HD * 2;      // 16 KB: one [128 x 64] bf16 tile
 constexpr int PT_BYTES = BLK * BLK * 2;       // 32 KB: [128 keys x 128 queries] bf16
 constexpr int QDO_STAGES = 2;
 constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + QDO_STAGES * 2 * TILE_BYTES /*Q,dO*/ + 2 * PT_BYTES /*P^T,dS^T*/ +
-                           QDO_STAGES * 2 * BLK * 4 /*lse2, D*/ + 1024 + 256;
+                           QDO_STAGES * 3 * BLK * 4 /*lse2, D, band start*/ + 1024 + 256;
+enum { MODE_DENSE = 0, MODE_BAND = 1, MODE_PIVOT = 2 };
 constexpr int NUM_THREADS = 192;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -44,13 +45,26 @@ struct BwdParams {
     const uint32_t* drop_mask;  // keep bits written by the forward, key-major ([b, heads, nkb*128, nqb, 4]: the 128 query
                                 // bits of (key, query block) are one 16-byte load for the thread that owns the key) or null
     float drop_scale;           // 1 / (1 - p)
+    // sparse training attention (mpu/sparse_transformer.py:675-725), two launches that share lse / delta / dq_acc:
+    //   MODE_BAND : keys = the sequence, key j visible to query i iff band_start(i) <= j <= i
+    //   MODE_PIVOT: keys = the gathered pivots (sk = n_piv rows), pivot visible iff piv_pos < band_start(i),
+    //               scores carry + log(s / n_piv); dK / dV rows go to the gathered scratch (kv_rows = n_piv)
+    int sk, kv_rows, sp_w, sp_times;
+    const int* piv_pos;         // [b, sk]
+    float piv_bias_log2;
 };
+
+__device__ __forceinline__ int band_start(int i, int w, int times) {
+    const int g = i / w - times + 1;
+    return g > 0 ? g * w : 0;
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
@@ -63,7 +77,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* sDST = sPT + PT_BYTES;
     float* sLse = reinterpret_cast<float*>(sDST + PT_BYTES);       // [stages][128]
     float* sDelta = sLse + QDO_STAGES * BLK;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + QDO_STAGES * BLK);
+    int* sBand = reinterpret_cast<int*>(sDelta + QDO_STAGES * BLK);   // [stages][128] band_start of the tile's queries
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBand + QDO_STAGES * BLK);
     uint64_t* kv_full = bars;                  // 1
     uint64_t* qdo_full = bars + 1;             // [2]
     uint64_t* qdo_empty = qdo_full + QDO_STAGES;
@@ -78,8 +93,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int kb = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
     const int k0 = kb * BLK;
     const int nqb = (p.s + BLK - 1) / BLK;
-    const int i_start = (k0 < p.sep_eff) ? 0 : kb;   // first query block that sees any key of this block
-    const int ntiles = nqb - i_start;
+    // query blocks that can see a key of this block
+    int i_start = (k0 < p.sep_eff) ? 0 : kb, i_end = nqb - 1;
+    if (MODE == MODE_BAND) {          // queries i with band_start(i) <= j <= i
+        i_start = kb;
+        i_end = min(nqb - 1, (((k0 + BLK - 1) / p.sp_w + p.sp_times) * p.sp_w - 1) / BLK);
+    } else if (MODE == MODE_PIVOT) {  // band_start(i) > 0  <=>  i >= sp_times * sp_w   (the host checks this is < s)
+        i_start = (p.sp_times * p.sp_w) / BLK;
+    }
+    const int ntiles = i_end - i_start + 1;
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
@@ -177,6 +199,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int epi_tid = threadIdx.x - 64;
         const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
         const float masked_val = -10000.0f * LOG2E;
+        const int my_pos = (MODE == MODE_PIVOT) ? (kj < p.sk ? p.piv_pos[(size_t)batch * p.sk + kj] : 0x7fffffff) : 0;
         const size_t stat_base = ((size_t)batch * p.heads + head) * p.s;
         const size_t keep_base = ((size_t)batch * p.heads + head) * (size_t)nqb * BLK;   // key rows are padded to blocks
         int stage = 0;
@@ -195,6 +218,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // publish them, then start the fetch for the next tile so its global-load latency is off the critical path
             sLse[stage * BLK + epi_tid] = pre_lse;
             sDelta[stage * BLK + epi_tid] = pre_delta;
+            if (MODE != MODE_DENSE) sBand[stage * BLK + epi_tid] = band_start(q0 + epi_tid, p.sp_w, p.sp_times);
             const uint4 kw = pre_keep;                  // this key's keep bits over the 128 queries of the tile
             if (t + 1 < ntiles) {
                 const int qn = q0 + BLK + epi_tid;
@@ -208,8 +232,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_wait(sdp_full, t & 1);
             tc_fence_after();
             if (t > 0) mbar_wait(pds_free, (t - 1) & 1);   // MMAs of the previous tile no longer read P^T / dS^T
-            const bool full_vis = (q0 + BLK <= p.s) && (k0 + BLK <= p.s) &&
-                                  ((k0 + BLK <= p.sep_eff) || (k0 + BLK - 1 <= q0));
+            bool full_vis = (q0 + BLK <= p.s) && (k0 + BLK <= p.s) &&
+                            ((k0 + BLK <= p.sep_eff) || (k0 + BLK - 1 <= q0));
+            if (MODE == MODE_BAND)      // every key of the block inside the band of every query of the tile
+                full_vis = (q0 + BLK <= p.s) && (k0 + BLK - 1 <= q0) &&
+                           (k0 >= band_start(q0 + BLK - 1, p.sp_w, p.sp_times));
+            if (MODE == MODE_PIVOT) full_vis = false;
+            const int* bnd = sBand + stage * BLK;
             const float* lse2 = sLse + stage * BLK;
             const float* dlt = sDelta + stage * BLK;
             const bool use_drop = p.drop_mask != nullptr;
@@ -252,8 +281,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         float pr;
                         if (full_vis) {
                             pr = exp2f(s2 - lse2[col]);
+                        } else if (MODE == MODE_PIVOT) {
+                            const bool vis = my_pos < bnd[col];
+                            s2 = vis ? s2 + p.piv_bias_log2 : masked_val;
+                            pr = (kj < p.sk && qi < p.s) ? exp2f(s2 - lse2[col]) : 0.f;
                         } else {
-                            const bool vis = (kj < p.sep_eff) || (kj <= qi);
+                            const bool vis = (MODE == MODE_BAND) ? (kj >= bnd[col] && kj <= qi)
+                                                                 : ((kj < p.sep_eff) || (kj <= qi));
                             if (!vis) s2 = masked_val;
                             pr = (kj < p.s && qi < p.s) ? exp2f(s2 - lse2[col]) : 0.f;
                         }
@@ -314,8 +348,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // (tcgen05.ld is warp-collective: every lane loads, only in-range rows store)
         {
             const int H3 = 3 * p.heads * HD;
-            const bool row_ok = kj < p.s;
-            __nv_bfloat16* base = p.dqkv + ((size_t)batch * p.s + (row_ok ? kj : 0)) * H3 + head * HD;
+            const bool row_ok = kj < p.kv_rows;
+            __nv_bfloat16* base = p.dqkv + ((size_t)batch * p.kv_rows + (row_ok ? kj : 0)) * H3 + head * HD;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
                 uint32_t r[HD];
@@ -438,14 +472,144 @@ extern "C" int cv_attn_bwd(const void* q, int64_t ldq, int64_t bsq, const void* 
     p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
     p.drop_mask = dropout_p > 0.f ? drop_mask : nullptr;
     p.drop_scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
+    p.sk = s; p.kv_rows = s; p.sp_w = 1; p.sp_times = 1; p.piv_pos = nullptr; p.piv_bias_log2 = 0.f;
     static bool attr_set = false;
     if (!attr_set) {
-        CV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<MODE_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     dim3 grid((s + BLK - 1) / BLK, heads, b);
-    attn_bwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, tmDO, p);
+    attn_bwd_kernel<MODE_DENSE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, tmDO, p);
     CV_LAUNCH_CHECK();
+    {
+        const size_t rows = (size_t)b * s;
+        const size_t n4 = rows * (h / 4);
+        size_t blocks = (n4 + 255) / 256;
+        size_t cap = (size_t)cvh::num_sms() * 8;
+        attn_bwd_dq_store_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+            dq_acc, static_cast<__nv_bfloat16*>(dqkv), rows, h);
+        CV_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the sparse training attention: band pass + gathered-pivot pass with the JOINT lse and
+// delta = rowsum(dO o O); the pivot pass' dK / dV are scattered back to the pivot positions
+// (oracle/sparse_decomposition.py: sparse_attention_two_pass_backward)
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void gather_pivots_bwd_kernel(const __nv_bfloat16* __restrict__ k, int64_t ldk, int64_t bsk,
+                                         const __nv_bfloat16* __restrict__ v, int64_t ldv, int64_t bsv,
+                                         const int64_t* __restrict__ pos, __nv_bfloat16* __restrict__ dst,
+                                         int* __restrict__ pos32, int n_piv, int h) {
+    const int row = blockIdx.x;
+    const int batch = row / n_piv;
+    const int64_t src = pos[row];
+    if (threadIdx.x == 0) pos32[row] = (int)src;
+    const uint4* ks = reinterpret_cast<const uint4*>(k + (size_t)batch * bsk + (size_t)src * ldk);
+    const uint4* vs = reinterpret_cast<const uint4*>(v + (size_t)batch * bsv + (size_t)src * ldv);
+    uint4* d = reinterpret_cast<uint4*>(dst + (size_t)row * 2 * h);
+    for (int i = threadIdx.x; i < h / 8; i += blockDim.x) {
+        d[i] = ks[i];
+        d[h / 8 + i] = vs[i];
+    }
+}
+
+// dqkv[b, pos[p], h:3h] += dpiv[b, p, h:3h]   (pivot positions of one sequence are distinct: no atomics)
+__global__ void scatter_pivot_grads_kernel(const __nv_bfloat16* __restrict__ dpiv, const int* __restrict__ pos32,
+                                           __nv_bfloat16* __restrict__ dqkv, int n_piv, int s, int h) {
+    const int row = blockIdx.x;
+    const int batch = row / n_piv;
+    const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(dpiv + (size_t)row * 3 * h + h);
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dqkv + ((size_t)batch * s + pos32[row]) * 3 * h + h);
+    for (int i = threadIdx.x; i < h; i += blockDim.x) {          // 2h bf16 = h pairs
+        const float2 a = __bfloat1622float2(dst[i]), c = __bfloat1622float2(src[i]);
+        dst[i] = __floats2bfloat162_rn(a.x + c.x, a.y + c.y);
+    }
+}
+inline size_t al256b(size_t x) { return (x + 255) / 256 * 256; }
+}  // namespace
+
+extern "C" int64_t cv_attn_sparse_bwd_workspace_bytes(int b, int heads, int head_dim, int s, int n_piv) {
+    const size_t h = (size_t)heads * head_dim;
+    return (int64_t)(al256b((size_t)b * s * h * 4) + al256b((size_t)b * heads * s * 4) + al256b((size_t)b * n_piv * 2 * h * 2) +
+                     al256b((size_t)b * n_piv * 3 * h * 2) + al256b((size_t)b * n_piv * 4));
+}
+
+extern "C" int cv_attn_sparse_bwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                                  const void* v, int64_t ldv, int64_t bsv, const int64_t* pivot_idx, const void* out,
+                                  const void* d_out, const float* lse, void* dqkv, void* workspace, int b, int heads,
+                                  int head_dim, int s, int n_piv, int query_window, int key_window_times,
+                                  void* stream) {
+    CV_REQUIRE(q && k && v && pivot_idx && out && d_out && lse && dqkv && workspace, "null pointer");
+    CV_REQUIRE(head_dim == HD, "head_dim must be 64");
+    CV_REQUIRE(b > 0 && heads > 0 && s > 0 && n_piv > 0 && n_piv <= s, "bad sizes");
+    CV_REQUIRE(query_window > 0 && key_window_times > 0 && s % query_window == 0,
+               "the sequence length must be a multiple of query_window");
+    CV_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0,
+               "strides must be multiples of 8 elements");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int h = heads * HD;
+    char* ws = static_cast<char*>(workspace);
+    float* dq_acc = reinterpret_cast<float*>(ws);
+    ws += al256b((size_t)b * s * h * 4);
+    float* delta = reinterpret_cast<float*>(ws);
+    ws += al256b((size_t)b * heads * s * 4);
+    __nv_bfloat16* pkv = reinterpret_cast<__nv_bfloat16*>(ws);
+    ws += al256b((size_t)b * n_piv * 2 * h * 2);
+    __nv_bfloat16* dpiv = reinterpret_cast<__nv_bfloat16*>(ws);
+    ws += al256b((size_t)b * n_piv * 3 * h * 2);
+    int* pos32 = reinterpret_cast<int*>(ws);
+    CV_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)b * s * h * sizeof(float), st));
+    {
+        const int n = b * s * heads;
+        attn_bwd_delta_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
+                                                              static_cast<const __nv_bfloat16*>(d_out), delta, b,
+                                                              heads, s);
+        CV_LAUNCH_CHECK();
+    }
+    gather_pivots_bwd_kernel<<<b * n_piv, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(k), ldk, bsk,
+                                                       static_cast<const __nv_bfloat16*>(v), ldv, bsv, pivot_idx, pkv,
+                                                       pos32, n_piv, h);
+    CV_LAUNCH_CHECK();
+    alignas(64) CUtensorMap tmQ, tmK, tmV, tmDO, tmPK, tmPV;
+    int rc;
+    if ((rc = encode_map3(&tmQ, q, b, s, h, ldq, bsq))) return rc;
+    if ((rc = encode_map3(&tmK, k, b, s, h, ldk, bsk))) return rc;
+    if ((rc = encode_map3(&tmV, v, b, s, h, ldv, bsv))) return rc;
+    if ((rc = encode_map3(&tmDO, d_out, b, s, h, h, (int64_t)s * h))) return rc;
+    if ((rc = encode_map3(&tmPK, pkv, b, n_piv, h, 2 * (int64_t)h, (int64_t)n_piv * 2 * h))) return rc;
+    if ((rc = encode_map3(&tmPV, pkv + h, b, n_piv, h, 2 * (int64_t)h, (int64_t)n_piv * 2 * h))) return rc;
+    BwdParams p;
+    p.b = b; p.heads = heads; p.s = s;
+    p.sep_eff = 0;
+    p.scale = 1.0f / sqrtf((float)head_dim);
+    p.scale_log2 = p.scale * LOG2E;
+    p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
+    p.drop_mask = nullptr; p.drop_scale = 1.0f;
+    p.sp_w = query_window; p.sp_times = key_window_times;
+    p.piv_bias_log2 = logf((float)(s / n_piv)) * LOG2E;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<MODE_BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<MODE_PIVOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    // band pass: dK / dV rows of the sequence
+    p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+    p.sk = s; p.kv_rows = s; p.piv_pos = nullptr;
+    attn_bwd_kernel<MODE_BAND><<<dim3((s + BLK - 1) / BLK, heads, b), NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, tmDO, p);
+    CV_LAUNCH_CHECK();
+    if (key_window_times * query_window < s) {       // some query sees pivots at all
+        p.dqkv = dpiv;
+        p.sk = n_piv; p.kv_rows = n_piv; p.piv_pos = pos32;
+        attn_bwd_kernel<MODE_PIVOT><<<dim3((n_piv + BLK - 1) / BLK, heads, b), NUM_THREADS, SMEM_BYTES, st>>>(
+            tmQ, tmPK, tmPV, tmDO, p);
+        CV_LAUNCH_CHECK();
+        scatter_pivot_grads_kernel<<<b * n_piv, 256, 0, st>>>(dpiv, pos32, static_cast<__nv_bfloat16*>(dqkv), n_piv, s, h);
+        CV_LAUNCH_CHECK();
+    }
     {
         const size_t rows = (size_t)b * s;
         const size_t n4 = rows * (h / 4);

@@ -33,7 +33,7 @@ constexpr int Q_BYTES = BQ * HD * 2;        // 16 KB
 constexpr int K_BYTES = BKV * HD * 2;       // 16 KB
 constexpr int V_BYTES = BKV * HD * 2;       // 16 KB
 constexpr int P_BYTES = BQ * BKV * 2;       // 32 KB (two 128x64 K-major sub-tiles)
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256 + 1024 /*sPos*/;
 constexpr int NUM_THREADS = 192;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -53,12 +53,25 @@ struct AttnParams {
                         //  [1] query-major [b, heads, nqb_all*128 (query), nkb_all, 4]: what this kernel consumes
     int nkb_all;        // ceil(sk / 128)
     int nqb_all;        // ceil(sq / 128)
+    // sparse training attention (mpu/sparse_transformer.py:675-725; sp_w = 0: dense).  One softmax over
+    //   band   : keys j with band_start(i) <= j <= i,  band_start(i) = max(0, i / sp_w - sp_times + 1) * sp_w
+    //   pivots : gathered keys p with piv_pos[p] < band_start(i), score + log(s / n_piv)
+    // (the closed form of the reference's window mask + rmask-gathered pivot mask, oracle/sparse_decomposition.py)
+    int sp_w, sp_times, n_piv;
+    const int* piv_pos;     // [b, n_piv] positions of the gathered pivot keys
+    float piv_bias_log2;    // log(s / n_piv) * log2(e)
 };
 
-template <bool DROPOUT>
+__device__ __forceinline__ int band_start(int i, int w, int times) {
+    const int g = i / w - times + 1;
+    return g > 0 ? g * w : 0;
+}
+
+template <bool DROPOUT, bool SPARSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmPK,
+                const __grid_constant__ CUtensorMap tmPV, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -72,6 +85,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* p_full = s_full + 2;           // [2]
     uint64_t* o_full = p_full + 2;           // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+    int* sPos = reinterpret_cast<int*>(bars + 32);           // [2][BKV] pivot positions of the current pivot tile
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // heaviest (last) query blocks first
@@ -82,7 +96,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     int kmax = q0 + BQ + p.off;              // exclusive bound of causally visible keys for the last row
     if (kmax < p.sep_eff) kmax = p.sep_eff;
     if (kmax > p.sk) kmax = p.sk;
-    const int nkb = (kmax + BKV - 1) / BKV;
+    int nkb = (kmax + BKV - 1) / BKV;
+    // sparse: band tiles jb0 .. jb0 + nband - 1 of the real keys first, then every pivot tile (if any query of the
+    // block can see a pivot at all); one tile list for the three roles
+    int jb0 = 0, nband = nkb;
+    if (SPARSE) {
+        const int q_last = min(q0 + BQ, p.sq) - 1;
+        jb0 = band_start(q0, p.sp_w, p.sp_times) / BKV;
+        nband = q_last / BKV - jb0 + 1;
+        const int npt = band_start(q_last, p.sp_w, p.sp_times) > 0 ? (p.n_piv + BKV - 1) / BKV : 0;
+        nkb = nband + npt;
+    }
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -109,8 +133,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mbar_wait(&kv_empty[stage], phase ^ 1);
                 uint8_t* sK = sKV + stage * (K_BYTES + V_BYTES);
                 mbar_expect_tx(&kv_full[stage], K_BYTES + V_BYTES);
-                tma_load_3d(sK, &tmK, &kv_full[stage], head * HD, j * BKV, batch);
-                tma_load_3d(sK + K_BYTES, &tmV, &kv_full[stage], head * HD, j * BKV, batch);
+                if (SPARSE && j >= nband) {
+                    tma_load_3d(sK, &tmPK, &kv_full[stage], head * HD, (j - nband) * BKV, batch);
+                    tma_load_3d(sK + K_BYTES, &tmPV, &kv_full[stage], head * HD, (j - nband) * BKV, batch);
+                } else {
+                    tma_load_3d(sK, &tmK, &kv_full[stage], head * HD, (jb0 + j) * BKV, batch);
+                    tma_load_3d(sK + K_BYTES, &tmV, &kv_full[stage], head * HD, (jb0 + j) * BKV, batch);
+                }
                 if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -164,6 +193,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int qi = q0 + row;                       // query index within the sequence
         const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
         const int causal_lim = qi + p.off;             // last causally visible key
+        const int bs_row = SPARSE ? band_start(qi, p.sp_w, p.sp_times) : 0;
         float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
         float o[HD];
 #pragma unroll
@@ -184,11 +214,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 kw = pre_keep;
                 if (j + 1 < nkb) pre_keep = keep_row[j + 1];
             }
+            const bool piv_tile = SPARSE && j >= nband;
+            if (piv_tile) {                             // positions of this tile's 128 gathered keys -> shared memory
+                const int pj = (j - nband) * BKV + row;
+                sPos[(j & 1) * BKV + row] = pj < p.n_piv ? p.piv_pos[(size_t)batch * p.n_piv + pj] : 0x7fffffff;
+                named_bar_sync(2, 128);
+            }
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            const int k0 = j * BKV;
+            const int k0 = SPARSE ? (piv_tile ? (j - nband) * BKV : (jb0 + j) * BKV) : j * BKV;
             // does this tile need per-element masking for this row?
-            const bool full_vis = (k0 + BKV <= p.sk) && ((k0 + BKV <= p.sep_eff) || (k0 + BKV - 1 <= causal_lim));
+            const bool full_vis = SPARSE ? (!piv_tile && k0 >= bs_row && k0 + BKV - 1 <= qi && k0 + BKV <= p.sk)
+                                         : (k0 + BKV <= p.sk) && ((k0 + BKV <= p.sep_eff) || (k0 + BKV - 1 <= causal_lim));
             float s[BKV];
 #pragma unroll
             for (int c = 0; c < BKV / 32; ++c) {
@@ -200,11 +237,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (full_vis) {
 #pragma unroll
                 for (int i = 0; i < BKV; ++i) { s[i] *= p.scale_log2; mx = fmaxf(mx, s[i]); }
+            } else if (piv_tile) {
+                const int* pos = sPos + (j & 1) * BKV;
+#pragma unroll
+                for (int i = 0; i < BKV; ++i) {
+                    const int pp = pos[i];
+                    float v = pp < bs_row ? s[i] * p.scale_log2 + p.piv_bias_log2 : masked_val;
+                    if (pp == 0x7fffffff) v = -INFINITY;   // beyond the pivot list
+                    s[i] = v;
+                    mx = fmaxf(mx, v);
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < BKV; ++i) {
                     const int kj = k0 + i;
-                    const bool vis = (kj < p.sep_eff) || (kj <= causal_lim);
+                    const bool vis = SPARSE ? (kj >= bs_row && kj <= qi) : ((kj < p.sep_eff) || (kj <= causal_lim));
                     float v = vis ? s[i] * p.scale_log2 : masked_val;
                     if (kj >= p.sk) v = -INFINITY;     // key does not exist
                     s[i] = v;
@@ -387,19 +434,99 @@ extern "C" int cv_attn_fwd(const void* q, int64_t ldq, int64_t bsq, const void* 
         p.nkb_all = (sk + BKV - 1) / BKV;
         p.nqb_all = (sq + BQ - 1) / BQ;
     }
+    p.sp_w = 0; p.sp_times = 0; p.n_piv = 0; p.piv_pos = nullptr; p.piv_bias_log2 = 0.f;
     static bool attr_set = false;
     if (!attr_set) {
-        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     dim3 grid((sq + BQ - 1) / BQ, heads, b);
     if (dropout_p > 0.f) {
         attn_dropout_mask_kernel<<<dim3(p.nqb_all, p.nkb_all, b * heads), 128, 0, s>>>(p);
         CV_LAUNCH_CHECK();
-        attn_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
+        attn_fwd_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, tmK, tmV, p);
     }
-    else attn_fwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, p);
+    else attn_fwd_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmQ, tmK, tmV, tmK, tmV, p);
+    CV_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse training attention (mpu/sparse_transformer.py:675-725): gathered pivots + causal band, one softmax
+// ------------------------------------------------------------------------------------------------
+namespace {
+// gathered pivot keys / values: dst[b, p, 0:h] = K[b, pos[p], :], dst[b, p, h:2h] = V[b, pos[p], :]; pos32 = (int)pos
+__global__ void gather_pivots_kernel(const __nv_bfloat16* __restrict__ k, int64_t ldk, int64_t bsk,
+                                     const __nv_bfloat16* __restrict__ v, int64_t ldv, int64_t bsv,
+                                     const int64_t* __restrict__ pos, __nv_bfloat16* __restrict__ dst,
+                                     int* __restrict__ pos32, int b, int n_piv, int h) {
+    const int row = blockIdx.x;                 // (batch, pivot)
+    const int batch = row / n_piv;
+    const int64_t src = pos[row];
+    if (threadIdx.x == 0) pos32[row] = (int)src;
+    const uint4* ks = reinterpret_cast<const uint4*>(k + (size_t)batch * bsk + (size_t)src * ldk);
+    const uint4* vs = reinterpret_cast<const uint4*>(v + (size_t)batch * bsv + (size_t)src * ldv);
+    uint4* d = reinterpret_cast<uint4*>(dst + (size_t)row * 2 * h);
+    for (int i = threadIdx.x; i < h / 8; i += blockDim.x) {
+        d[i] = ks[i];
+        d[h / 8 + i] = vs[i];
+    }
+}
+}  // namespace
+
+extern "C" int64_t cv_attn_sparse_workspace_bytes(int b, int heads, int head_dim, int n_piv) {
+    const int64_t h = (int64_t)heads * head_dim;
+    return ((int64_t)b * n_piv * 2 * h * 2 + 255) / 256 * 256 + (int64_t)b * n_piv * 4;
+}
+
+extern "C" int cv_attn_sparse_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                                  const void* v, int64_t ldv, int64_t bsv, const int64_t* pivot_idx, void* out,
+                                  int64_t ldo, int64_t bso, float* lse, void* workspace, int b, int heads,
+                                  int head_dim, int s, int n_piv, int query_window, int key_window_times,
+                                  void* stream) {
+    CV_REQUIRE(q && k && v && pivot_idx && out && workspace, "null pointer");
+    CV_REQUIRE(head_dim == HD, "head_dim must be 64 (CogView: hidden / heads = 64)");
+    CV_REQUIRE(b > 0 && heads > 0 && s > 0 && n_piv > 0 && n_piv <= s, "bad sizes");
+    CV_REQUIRE(query_window > 0 && key_window_times > 0 && s % query_window == 0,
+               "the sequence length must be a multiple of query_window (mpu/sparse_transformer.py:703,713)");
+    CV_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && bsq % 8 == 0 && bsk % 8 == 0 &&
+                   bsv % 8 == 0 && bso % 8 == 0,
+               "strides must be multiples of 8 elements");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int h = heads * HD;
+    __nv_bfloat16* pkv = static_cast<__nv_bfloat16*>(workspace);
+    int* pos32 = reinterpret_cast<int*>(static_cast<char*>(workspace) + ((size_t)b * n_piv * 2 * h * 2 + 255) / 256 * 256);
+    gather_pivots_kernel<<<b * n_piv, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(k), ldk, bsk,
+                                                   static_cast<const __nv_bfloat16*>(v), ldv, bsv, pivot_idx, pkv, pos32,
+                                                   b, n_piv, h);
+    CV_LAUNCH_CHECK();
+    alignas(64) CUtensorMap tmQ, tmK, tmV, tmPK, tmPV;
+    int rc;
+    if ((rc = encode_qkv_map(&tmQ, q, b, s, h, ldq, bsq, BQ))) return rc;
+    if ((rc = encode_qkv_map(&tmK, k, b, s, h, ldk, bsk, BKV))) return rc;
+    if ((rc = encode_qkv_map(&tmV, v, b, s, h, ldv, bsv, BKV))) return rc;
+    if ((rc = encode_qkv_map(&tmPK, pkv, b, n_piv, h, 2 * (int64_t)h, (int64_t)n_piv * 2 * h, BKV))) return rc;
+    if ((rc = encode_qkv_map(&tmPV, pkv + h, b, n_piv, h, 2 * (int64_t)h, (int64_t)n_piv * 2 * h, BKV))) return rc;
+    AttnParams p;
+    p.b = b; p.heads = heads; p.sq = s; p.sk = s;
+    p.off = 0; p.sep_eff = 0;
+    p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * LOG2E;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo; p.bso = bso; p.lse = lse;
+    p.drop.p = 0.f; p.drop.scale = 1.f; p.drop.threshold = 0; p.drop.stream = 0; p.drop.seed = 0;
+    p.drop_mask = nullptr;
+    p.nkb_all = (s + BKV - 1) / BKV;
+    p.nqb_all = (s + BQ - 1) / BQ;
+    p.sp_w = query_window; p.sp_times = key_window_times; p.n_piv = n_piv; p.piv_pos = pos32;
+    p.piv_bias_log2 = logf((float)(s / n_piv)) * LOG2E;           // integer division as in :697
+    static bool attr_set = false;
+    if (!attr_set) {
+        CV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid((s + BQ - 1) / BQ, heads, b);
+    attn_fwd_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, tmPK, tmPV, p);
     CV_LAUNCH_CHECK();
     return 0;
 }

@@ -31,6 +31,8 @@
 //
 // Everything exchanged between CTAs goes through L2 (ld.global.cg / st + fence + grid barrier): L1 is not coherent
 // and there is no kernel boundary to invalidate it.
+#include <type_traits>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/cogview_b200.h"
@@ -39,16 +41,17 @@ namespace {
 using namespace cv;
 typedef __nv_bfloat16 bf16;
 
-constexpr int CW = 8;               // consumer warps
+constexpr int CW = 16;              // consumer warps: two groups of GW that take alternate ring stages
+constexpr int GW = 8;               // warps per group = K slices of a stage
 constexpr int CT = CW * 32;         // consumer threads
 constexpr int NT = CT + 32;         // + one producer warp
 constexpr int TILE = 16;            // weight rows (output columns) per MMA tile
 constexpr int KG = 4;               // K groups of the 4h->h matrix
 constexpr int HD = 64;              // head dim
 constexpr int MAXST = 8;            // ring stages (upper bound)
-constexpr int NE = 5;               // bf16 pairs per thread and row in the glue: h <= 2 * CT * NE = 2560
+constexpr int NV = 2;               // 4-column vectors per thread and row in the glue: h <= 4 * CT * NV = 4096
 constexpr int MAXM = 8;
-constexpr int AUNR = 8;             // attention: 4-key groups in flight per warp iteration (32 keys)
+constexpr int AUNR = 4;             // attention: 4-key groups in flight per warp iteration (16 keys)
 constexpr int PART_STRIDE = HD + 2; // attention partial: acc[64], m, l
 
 struct Params {
@@ -68,8 +71,9 @@ struct Params {
     unsigned int *attn_cnt, *fc2_cnt;
     unsigned long long *bar_ctr, *bar_base;
     int* err;
+    unsigned long long* prof;      // optional [grid][L][16] globaltimer stamps of the phase boundaries
     // derived on the host
-    int kstage, nst, stage_bytes, pitch, xpitch, S;
+    int kstage, nst, stage_bytes, pitch, xpitch, S, quiet;
     float scale_log2;
 };
 
@@ -158,9 +162,10 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
     const int nks = h / p.kstage;
 
     if (tid == 0) {
+        flags[1] = p.quiet;
         for (int i = 0; i < p.nst; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], CW);
+            mbar_init(&empty[i], GW);
         }
         fence_barrier_init();
     }
@@ -178,6 +183,9 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 const int rows = min(TILE, m.r1 - r);
                 for (int ks = 0; ks < nks; ++ks) {
                     mbar_wait(&empty[st], ph ^ 1);
+                    if (p.quiet) {      // experiment: no weight traffic while the consumers are in a latency phase
+                        while (*reinterpret_cast<volatile int*>(&flags[1]) != 0) __nanosleep(64);
+                    }
                     if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)(rows * p.kstage * 2));
                     __syncwarp();
                     if (lane < rows)
@@ -203,16 +211,20 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
     // consumer warps
     // ============================================================================================
     const int g = lane >> 2, q = lane & 3;
-    const int kpw = p.kstage / CW;                 // k elements per warp and stage ( = 32 * CPW )
+    const int kpw = p.kstage / GW;                 // k elements per warp and stage ( = 32 * CPW )
+    const int grp_w = warp / GW, wg = warp % GW;   // stage group, K slice inside a stage
     unsigned long long bar_target = *reinterpret_cast<volatile unsigned long long*>(p.bar_base);
     const int t_cached = __ldg(p.cur_len);         // tokens cached before this step; the new token sits at index t
-    int st = 0, pbuf = 0;
+    int st = 0, pbuf = 0, sq = 0;
     uint32_t ph = 0;
 
     // rows >= M of the activation operand stay zero for the whole kernel
     for (int i = tid; i < MAXM * p.xpitch / 16; i += CT) sts128(xop + i * 16, make_uint4(0, 0, 0, 0));
     named_bar_sync(1, CT);
 
+    auto stamp = [&](int l, int slot) {
+        if (p.prof != nullptr && tid == 0) p.prof[((size_t)cta * p.L + l) * 16 + slot] = global_timer_ns();
+    };
     auto grid_barrier = [&](int code) {
         named_bar_sync(1, CT);
         if (tid == 0) {
@@ -237,28 +249,34 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
         named_bar_sync(1, CT);
     };
 
-    // y[m, n] for the CTA's rows of one matrix, x = the shared-memory operand
+    // y[m, n] for the CTA's rows of one matrix, x = the shared-memory operand.  Ring stages alternate between the two
+    // warp groups (stage counter `sq` is the producer's), so two stages are in work at any time; every warp keeps its
+    // partial [16 x 8] tile and the 16 partials of a tile are summed through shared memory.
     auto consume = [&](const Mat& m, int epi, const bf16* bias, void* out, int64_t ldo) {
+        if (p.quiet && tid == 0) *reinterpret_cast<volatile int*>(&flags[1]) = 0;
         for (int r = m.r0; r < m.r1; r += TILE) {
             float d[4] = {0.f, 0.f, 0.f, 0.f};
             for (int ks = 0; ks < nks; ++ks) {
-                mbar_wait(&full[st], ph);
-                const uint32_t wa = ring + st * p.stage_bytes + g * p.pitch + (warp * kpw + q * 8) * 2;
-                const uint32_t xa = xop + g * p.xpitch + (ks * p.kstage + warp * kpw + q * 8) * 2;
-                uint4 w0[CPW], w1[CPW], xv[CPW];
+                if ((sq & 1) == grp_w) {
+                    mbar_wait(&full[st], ph);
+                    const uint32_t wa = ring + st * p.stage_bytes + g * p.pitch + (wg * kpw + q * 8) * 2;
+                    const uint32_t xa = xop + g * p.xpitch + (ks * p.kstage + wg * kpw + q * 8) * 2;
+                    uint4 w0[CPW], w1[CPW], xv[CPW];
 #pragma unroll
-                for (int c = 0; c < CPW; ++c) {
-                    w0[c] = lds128(wa + c * 64);
-                    w1[c] = lds128(wa + 8 * p.pitch + c * 64);
-                    xv[c] = lds128(xa + c * 64);
-                }
+                    for (int c = 0; c < CPW; ++c) {
+                        w0[c] = lds128(wa + c * 64);
+                        w1[c] = lds128(wa + 8 * p.pitch + c * 64);
+                        xv[c] = lds128(xa + c * 64);
+                    }
 #pragma unroll
-                for (int c = 0; c < CPW; ++c) {
-                    mma_16816(d, w0[c].x, w1[c].x, w0[c].y, w1[c].y, xv[c].x, xv[c].y);
-                    mma_16816(d, w0[c].z, w1[c].z, w0[c].w, w1[c].w, xv[c].z, xv[c].w);
+                    for (int c = 0; c < CPW; ++c) {
+                        mma_16816(d, w0[c].x, w1[c].x, w0[c].y, w1[c].y, xv[c].x, xv[c].y);
+                        mma_16816(d, w0[c].z, w1[c].z, w0[c].w, w1[c].w, xv[c].z, xv[c].w);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[st]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[st]);
+                ++sq;
                 if (++st == p.nst) { st = 0; ph ^= 1; }
             }
             // D fragment: d0,d1 = (row g, cols 2q,2q+1), d2,d3 = (row g+8, ...); row = output column, col = sequence
@@ -286,6 +304,7 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
             }
             pbuf ^= 1;
         }
+        if (p.quiet && tid == 0) *reinterpret_cast<volatile int*>(&flags[1]) = 1;
     };
 
     // x operand <- M rows of h bf16 values written by other CTAs
@@ -302,22 +321,38 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
     //   v  = res + LN_post(gemm_out / (max|gemm_out| / 8))          (skipped when gemm_out == nullptr)
     //   xn = LN_pre(v / (max|v| / 8))  -> shared-memory operand;   v -> res_out (this CTA's column slice only)
     // res = res_in (fp32, L2) or, when res_in == nullptr, the embedding wte[ids] + wpe[pos].
-    auto glue = [&](const bf16* gemm_out, const bf16* g_post, const bf16* b_post, float eps_post, const float* res_in,
-                    float* res_out, const bf16* g_pre, const bf16* b_pre, float eps_pre) {
+    // A thread owns the 4-column vectors tid + 256 j of every row (8-byte bf16 / 16-byte fp32 accesses); the phase is
+    // bound by instruction issue (2 warps per scheduler), so the code is kept to ~12 instructions per element.
+    int prof_layer = -1;       // >= 0: sub-stamps of the glue go to slots 13..15 of this layer
+    auto glue = [&](auto emb_tag, const bf16* gemm_out, const bf16* g_post, const bf16* b_post, float eps_post,
+                    const float* res_in, float* res_out, const bf16* g_pre, const bf16* b_pre, float eps_pre) {
+        constexpr bool EMB = decltype(emb_tag)::value;      // residual = embedding of the new token (layer 0)
+        const int hv = h >> 2;
         const float inv_h = 1.0f / h;
-        uint32_t gq[NE], bq[NE];
+        bool ok[NV];
+        uint2 gq[NV], bq[NV];
 #pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const int col = 2 * (tid + CT * e);
-            const bool ok = col < h;
-            gq[e] = ok ? __ldg(reinterpret_cast<const unsigned int*>(g_pre + col)) : 0u;
-            bq[e] = ok ? __ldg(reinterpret_cast<const unsigned int*>(b_pre + col)) : 0u;
+        for (int j = 0; j < NV; ++j) {
+            const int vi = tid + CT * j;
+            ok[j] = vi < hv;
+            gq[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(g_pre) + vi) : make_uint2(0u, 0u);
+            bq[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(b_pre) + vi) : make_uint2(0u, 0u);
         }
-        auto residual = [&](int mi, int col) -> float2 {
-            if (res_in != nullptr) return __ldcg(reinterpret_cast<const float2*>(res_in + (size_t)mi * h + col));
-            const uint32_t a = __ldg(reinterpret_cast<const unsigned int*>(p.wte + (size_t)__ldg(p.ids + mi) * h + col));
-            const uint32_t b = __ldg(reinterpret_cast<const unsigned int*>(p.wpe + (size_t)__ldg(p.pos + mi) * h + col));
-            return make_float2(bflo(a) + bflo(b), bfhi(a) + bfhi(b));
+        const uint2* wrow[EMB ? MR : 1];
+        const uint2* prow[EMB ? MR : 1];
+        if (EMB) {
+#pragma unroll
+            for (int mi = 0; mi < MR; ++mi) {
+                const int mc = mi < M ? mi : 0;
+                wrow[EMB ? mi : 0] = reinterpret_cast<const uint2*>(p.wte + (size_t)__ldg(p.ids + mc) * h);
+                prow[EMB ? mi : 0] = reinterpret_cast<const uint2*>(p.wpe + (size_t)__ldg(p.pos + mc) * h);
+            }
+        }
+        auto residual = [&](int mi, int vi) -> float4 {
+            if (!EMB) return __ldcg(reinterpret_cast<const float4*>(res_in) + mi * hv + vi);
+            const uint2 a = __ldg(wrow[EMB ? mi : 0] + vi);
+            const uint2 b = __ldg(prow[EMB ? mi : 0] + vi);
+            return make_float4(bflo(a.x) + bflo(b.x), bfhi(a.x) + bfhi(b.x), bflo(a.y) + bflo(b.y), bfhi(a.y) + bfhi(b.y));
         };
         // block-wide: s[m] <- sum over the row, mx <- max over everything; one named barrier
         auto reduce = [&](float (&s)[MR], float& mx, int which) {
@@ -343,41 +378,47 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
             for (int w = 0; w < CW; ++w) t = fmaxf(t, red[(which * CW + w) * (MAXM + 1) + MAXM]);
             mx = t;
         };
+        auto sum4 = [](const float4& a) { return (a.x + a.y) + (a.z + a.w); };
+        auto amax4 = [](const float4& a) { return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))); };
+        auto dev4 = [](const float4& a, float mean) {
+            const float x = a.x - mean, y = a.y - mean, z = a.z - mean, w = a.w - mean;
+            return (x * x + y * y) + (z * z + w * w);
+        };
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        float2 v[MR][NE];
+        float4 v[MR][NV];
         if (gemm_out != nullptr) {
-            uint32_t gp[NE], bp[NE];
+            uint2 gp[NV], bp[NV];
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const int col = 2 * (tid + CT * e);
-                const bool ok = col < h;
-                gp[e] = ok ? __ldg(reinterpret_cast<const unsigned int*>(g_post + col)) : 0u;
-                bp[e] = ok ? __ldg(reinterpret_cast<const unsigned int*>(b_post + col)) : 0u;
+            for (int j = 0; j < NV; ++j) {
+                const int vi = tid + CT * j;
+                gp[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(g_post) + vi) : make_uint2(0u, 0u);
+                bp[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(b_post) + vi) : make_uint2(0u, 0u);
             }
             float s[MR], amax = 0.f;
 #pragma unroll
             for (int mi = 0; mi < MR; ++mi) {
                 s[mi] = 0.f;
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    const int col = 2 * (tid + CT * e);
-                    const uint32_t u = (mi < M && col < h) ? ldcg_u32(gemm_out + (size_t)mi * h + col) : 0u;
-                    v[mi][e] = make_float2(bflo(u), bfhi(u));
-                    s[mi] += v[mi][e].x + v[mi][e].y;
-                    amax = fmaxf(amax, fmaxf(fabsf(v[mi][e].x), fabsf(v[mi][e].y)));
+                for (int j = 0; j < NV; ++j) {
+                    uint2 u = make_uint2(0u, 0u);
+                    if (mi < M && ok[j]) u = __ldcg(reinterpret_cast<const uint2*>(gemm_out) + mi * hv + tid + CT * j);
+                    v[mi][j] = make_float4(bflo(u.x), bfhi(u.x), bflo(u.y), bfhi(u.y));
+                    s[mi] += sum4(v[mi][j]);
+                    amax = fmaxf(amax, amax4(v[mi][j]));
                 }
             }
-            float2 rs[MR == 4 ? MR : 1][NE];      // small batches: fetch the residual under the first reduction
-            if (MR == 4) {
+            constexpr bool PRE = MR <= 4;               // small batches: the residual is fetched under the first reduction
+            float4 rs[PRE ? MR : 1][NV];
+            if (PRE) {
 #pragma unroll
                 for (int mi = 0; mi < MR; ++mi)
 #pragma unroll
-                    for (int e = 0; e < NE; ++e) {
-                        const int col = 2 * (tid + CT * e);
-                        rs[MR == 4 ? mi : 0][e] = (mi < M && col < h) ? residual(mi, col) : make_float2(0.f, 0.f);
-                    }
+                    for (int j = 0; j < NV; ++j)
+                        rs[PRE ? mi : 0][j] = (mi < M && ok[j]) ? residual(mi, tid + CT * j) : zero4;
             }
             reduce(s, amax, 0);
+            if (prof_layer >= 0) stamp(prof_layer, 13);
             const float c = amax * 0.125f;
             float ss[MR], dummy = 0.f;
 #pragma unroll
@@ -385,12 +426,8 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 const float mean = s[mi] * inv_h;
                 ss[mi] = 0.f;
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    if (2 * (tid + CT * e) < h) {
-                        const float a = v[mi][e].x - mean, b = v[mi][e].y - mean;
-                        ss[mi] += a * a + b * b;
-                    }
-                }
+                for (int j = 0; j < NV; ++j)
+                    if (ok[j]) ss[mi] += dev4(v[mi][j], mean);
             }
             reduce(ss, dummy, 1);
 #pragma unroll
@@ -398,69 +435,72 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 const float mean = s[mi] * inv_h;
                 const float rstd = rsqrtf(ss[mi] * inv_h + eps_post * c * c);
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    const int col = 2 * (tid + CT * e);
-                    float2 r;
-                    if (MR == 4) r = rs[MR == 4 ? mi : 0][e];
-                    else r = (mi < M && col < h) ? residual(mi, col) : make_float2(0.f, 0.f);
-                    v[mi][e].x = (v[mi][e].x - mean) * rstd * bflo(gp[e]) + bflo(bp[e]) + r.x;
-                    v[mi][e].y = (v[mi][e].y - mean) * rstd * bfhi(gp[e]) + bfhi(bp[e]) + r.y;
+                for (int j = 0; j < NV; ++j) {
+                    float4& a = v[mi][j];
+                    const float4 r = PRE ? rs[PRE ? mi : 0][j] : ((mi < M && ok[j]) ? residual(mi, tid + CT * j) : zero4);
+                    a.x = (a.x - mean) * rstd * bflo(gp[j].x) + bflo(bp[j].x) + r.x;
+                    a.y = (a.y - mean) * rstd * bfhi(gp[j].x) + bfhi(bp[j].x) + r.y;
+                    a.z = (a.z - mean) * rstd * bflo(gp[j].y) + bflo(bp[j].y) + r.z;
+                    a.w = (a.w - mean) * rstd * bfhi(gp[j].y) + bfhi(bp[j].y) + r.w;
                 }
             }
         } else {
 #pragma unroll
             for (int mi = 0; mi < MR; ++mi)
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    const int col = 2 * (tid + CT * e);
-                    v[mi][e] = (mi < M && col < h) ? residual(mi, col) : make_float2(0.f, 0.f);
-                }
+                for (int j = 0; j < NV; ++j) v[mi][j] = (mi < M && ok[j]) ? residual(mi, tid + CT * j) : zero4;
         }
         // residual stream out (owner slice), statistics of v
-        const int np = h / 2;
-        const int p_lo = (int)(((int64_t)np * cta) / G), p_hi = (int)(((int64_t)np * (cta + 1)) / G);
+        const int v_lo = (int)(((int64_t)hv * cta) / G), v_hi = (int)(((int64_t)hv * (cta + 1)) / G);
         float s2[MR], amax2 = 0.f;
 #pragma unroll
         for (int mi = 0; mi < MR; ++mi) {
             s2[mi] = 0.f;
+            if (mi < M) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const int pi = tid + CT * e;
-                if (mi < M && pi < np) {
-                    if (res_out != nullptr && pi >= p_lo && pi < p_hi)
-                        *reinterpret_cast<float2*>(res_out + (size_t)mi * h + 2 * pi) = v[mi][e];
-                    s2[mi] += v[mi][e].x + v[mi][e].y;
-                    amax2 = fmaxf(amax2, fmaxf(fabsf(v[mi][e].x), fabsf(v[mi][e].y)));
+                for (int j = 0; j < NV; ++j) {
+                    const int vi = tid + CT * j;
+                    if (ok[j]) {
+                        if (res_out != nullptr && vi >= v_lo && vi < v_hi)
+                            *(reinterpret_cast<float4*>(res_out) + mi * hv + vi) = v[mi][j];
+                        s2[mi] += sum4(v[mi][j]);
+                        amax2 = fmaxf(amax2, amax4(v[mi][j]));
+                    }
                 }
             }
         }
         reduce(s2, amax2, 2);
+        if (prof_layer >= 0) stamp(prof_layer, 14);
         const float c2 = amax2 * 0.125f;
         float ss2[MR], dummy2 = 0.f;
 #pragma unroll
         for (int mi = 0; mi < MR; ++mi) {
             const float mean = s2[mi] * inv_h;
             ss2[mi] = 0.f;
+            if (mi < M) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                if (mi < M && tid + CT * e < np) {
-                    const float a = v[mi][e].x - mean, b = v[mi][e].y - mean;
-                    ss2[mi] += a * a + b * b;
-                }
+                for (int j = 0; j < NV; ++j)
+                    if (ok[j]) ss2[mi] += dev4(v[mi][j], mean);
             }
         }
         reduce(ss2, dummy2, 3);
+        if (prof_layer >= 0) stamp(prof_layer, 15);
 #pragma unroll
         for (int mi = 0; mi < MR; ++mi) {
-            const float mean = s2[mi] * inv_h;
-            const float rstd = rsqrtf(ss2[mi] * inv_h + eps_pre * c2 * c2);
+            if (mi < M) {
+                const float mean = s2[mi] * inv_h;
+                const float rstd = rsqrtf(ss2[mi] * inv_h + eps_pre * c2 * c2);
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const int pi = tid + CT * e;
-                if (mi < M && pi < np) {
-                    const float a = (v[mi][e].x - mean) * rstd * bflo(gq[e]) + bflo(bq[e]);
-                    const float b = (v[mi][e].y - mean) * rstd * bfhi(gq[e]) + bfhi(bq[e]);
-                    sts32(xop + mi * p.xpitch + pi * 4, pack_bf16x2(a, b));
+                for (int j = 0; j < NV; ++j) {
+                    if (ok[j]) {
+                        const float4 a = v[mi][j];
+                        const uint32_t lo = pack_bf16x2((a.x - mean) * rstd * bflo(gq[j].x) + bflo(bq[j].x),
+                                                        (a.y - mean) * rstd * bfhi(gq[j].x) + bfhi(bq[j].x));
+                        const uint32_t hi = pack_bf16x2((a.z - mean) * rstd * bflo(gq[j].y) + bflo(bq[j].y),
+                                                        (a.w - mean) * rstd * bfhi(gq[j].y) + bfhi(bq[j].y));
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xop + mi * p.xpitch + (tid + CT * j) * 8),
+                                     "r"(lo), "r"(hi) : "memory");
+                    }
                 }
             }
         }
@@ -595,21 +635,39 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
     const bf16* prev_post_b = nullptr;
     for (int l = 0; l < p.L; ++l) {
         const cv_decode_layer& Lw = p.layers[l];
+        stamp(l, 0);
         // x = x_prev + LN4(mlp_out_prev)  (layer 0: the embedding);  xn = LN1(x)
-        glue(l == 0 ? nullptr : p.mlp_out, prev_post_g, prev_post_b, p.eps, l == 0 ? nullptr : p.resid_a, p.resid_b,
-             static_cast<const bf16*>(Lw.ln1_g), static_cast<const bf16*>(Lw.ln1_b), p.eps);
+        if (l == 0)
+            glue(std::true_type{}, nullptr, nullptr, nullptr, p.eps, nullptr, p.resid_b,
+                 static_cast<const bf16*>(Lw.ln1_g), static_cast<const bf16*>(Lw.ln1_b), p.eps);
+        else {
+            prof_layer = l;
+            glue(std::false_type{}, p.mlp_out, prev_post_g, prev_post_b, p.eps, p.resid_a, p.resid_b,
+                 static_cast<const bf16*>(Lw.ln1_g), static_cast<const bf16*>(Lw.ln1_b), p.eps);
+            prof_layer = -1;
+        }
+        stamp(l, 1);
         consume(make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0), EPI_BF16, static_cast<const bf16*>(Lw.b_qkv), p.qkv, 3 * h);
+        stamp(l, 2);
         grid_barrier(100 + l);
+        stamp(l, 3);
         attention(l);
+        stamp(l, 4);
         grid_barrier(200 + l);
+        stamp(l, 5);
         load_x(p.ctx, h, 0);
         consume(make_mat(Lw.w_dense, h, h, cta, G, 0), EPI_BF16, static_cast<const bf16*>(Lw.b_dense), p.attn_out, h);
+        stamp(l, 6);
         grid_barrier(300 + l);
+        stamp(l, 7);
         // y = x + LN3(attn_out);  xn2 = LN2(y)
-        glue(p.attn_out, static_cast<const bf16*>(Lw.ln3_g), static_cast<const bf16*>(Lw.ln3_b), p.eps, p.resid_b,
+        glue(std::false_type{}, p.attn_out, static_cast<const bf16*>(Lw.ln3_g), static_cast<const bf16*>(Lw.ln3_b), p.eps, p.resid_b,
              p.resid_a, static_cast<const bf16*>(Lw.ln2_g), static_cast<const bf16*>(Lw.ln2_b), p.eps);
+        stamp(l, 8);
         consume(make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0), EPI_BF16_GELU, static_cast<const bf16*>(Lw.b_fc1), p.h4, 4 * h);
+        stamp(l, 9);
         grid_barrier(400 + l);
+        stamp(l, 10);
         {
             const int rg = cta / KG, kg = cta % KG;
             load_x(p.h4, 4 * h, kg * h);
@@ -636,12 +694,14 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 }
             }
         }
+        stamp(l, 11);
         grid_barrier(500 + l);
+        stamp(l, 12);
         prev_post_g = static_cast<const bf16*>(Lw.ln4_g);
         prev_post_b = static_cast<const bf16*>(Lw.ln4_b);
     }
     // final: x = x + LN4(mlp_out);  logits = LN_f(x) wte^T
-    glue(p.mlp_out, prev_post_g, prev_post_b, p.eps, p.resid_a, nullptr, p.lnf_g, p.lnf_b, p.eps_final);
+    glue(std::false_type{}, p.mlp_out, prev_post_g, prev_post_b, p.eps, p.resid_a, nullptr, p.lnf_g, p.lnf_b, p.eps_final);
     consume(make_mat(p.wte, h, p.V, cta, G, 0), EPI_F32, nullptr, p.logits, p.ldl);
     if (cta == 0 && tid == 0) *p.bar_base = bar_target;
 }
@@ -690,7 +750,7 @@ extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
                "null pointer");
     const int h = a->hidden, heads = a->heads, M = a->batch;
     CV_REQUIRE(M >= 1 && M <= MAXM, "cv_decode_step handles 1 <= batch <= 8 sequences");
-    CV_REQUIRE(h > 0 && h % 256 == 0 && h <= 2 * CT * NE, "hidden must be a multiple of 256 and <= 2560");
+    CV_REQUIRE(h > 0 && h % 256 == 0 && h <= 2560, "hidden must be a multiple of 256 and <= 2560");
     CV_REQUIRE(heads > 0 && heads * HD == h && heads <= (1024 / MAXM), "hidden must be heads * 64");
     CV_REQUIRE(a->num_layers >= 1 && a->vocab >= 1 && a->max_len >= 1 && a->ld_logits >= a->vocab, "bad sizes");
     CV_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "workspace must be 256-byte aligned");
@@ -708,6 +768,7 @@ extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
     p.cache = static_cast<bf16*>(a->cache);
     p.cache_ls = a->cache_layer_stride; p.cache_bs = a->cache_batch_stride;
     p.logits = a->logits; p.ldl = a->ld_logits;
+    p.prof = static_cast<unsigned long long*>(a->prof);
     char* ws = static_cast<char*>(a->workspace);
     const WsLayout w = ws_layout(h, heads);
     p.bar_ctr = reinterpret_cast<unsigned long long*>(ws + WS_CTR);
@@ -735,6 +796,14 @@ extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
     CV_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     int nst = (max_smem - fixed - 1024) / p.stage_bytes;
     if (nst > MAXST) nst = MAXST;
+    if (const char* e = getenv("COGVIEW_B200_STEP_NST")) {
+        const int cap = atoi(e);
+        if (cap >= 2 && cap < nst) nst = cap;
+    }
+    {
+        const char* e = getenv("COGVIEW_B200_STEP_QUIET");
+        p.quiet = (e && e[0] == '1') ? 1 : 0;
+    }
     CV_REQUIRE(nst >= 2, "not enough shared memory for the weight ring");
     p.nst = nst;
     const size_t smem_bytes = (size_t)fixed + (size_t)nst * p.stage_bytes;

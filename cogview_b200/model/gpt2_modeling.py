@@ -80,12 +80,10 @@ class GPT2Model(torch.nn.Module):
         """Same positional arguments as the reference (model/gpt2_modeling.py:106).  Returns
         (logits [b, s, V] fp32, *mems).  `logits_last_only` (keyword, extension): only the last position's
         logits are computed — what the sampling loop reads (generation/sampling.py:155)."""
-        if is_sparse == 1:
-            raise NotImplementedError('sparse training (is_sparse=1) is not implemented in this round')
         tr = self.transformer
         b, sq = input_ids.shape
         mem_len = mems[0].size(1) if mems else 0
-        sep = 0 if is_sparse == 2 else mask_to_sep(attention_mask, sq, sq + mem_len)
+        sep = 0 if is_sparse != 0 else mask_to_sep(attention_mask, sq, sq + mem_len)
         if position_ids.shape != input_ids.shape:
             position_ids = position_ids.expand_as(input_ids)
         fast = self._fast_decode(input_ids, position_ids, mems, b, sq) if is_sparse == 0 else None

@@ -293,15 +293,22 @@ class GPT2ParallelSelfAttention(torch.nn.Module):
         self.output_dropout = torch.nn.Dropout(output_dropout_prob)
 
     def forward(self, hidden_states, ltor_mask, pivot_idx=None, is_sparse=0, mem=None):
-        """Standalone (unfused) use: hidden_states [b, s, h] already layer-normed; inference only for mem."""
-        if is_sparse != 0:
-            raise NotImplementedError('sparse attention (is_sparse=%d) is not implemented in this round' % is_sparse)
+        """Standalone (unfused) use: hidden_states [b, s, h] already layer-normed; inference only for mem.
+        is_sparse == 1 (mpu/sparse_transformer.py:150-151): `ltor_mask` is the reference's pivot_attention_mask
+        (rmask gathered at pivot_idx, :569) — the kernel evaluates that mask in closed form from pivot_idx."""
+        if is_sparse not in (0, 1):
+            raise NotImplementedError('is_sparse=2 runs through GPT2ParallelTransformer (K|V cache + cv_attn_gather)')
         b, sq, h = hidden_states.shape
         heads = self.num_attention_heads_per_partition
         src = hidden_states if mem is None else torch.cat((mem, hidden_states), 1)
         mixed = self.query_key_value(src)
         sk = src.shape[1]
-        sep = mask_to_sep(ltor_mask, sq, sk)
+        if is_sparse == 1:
+            if mem is not None or pivot_idx is None:
+                raise ValueError('sparse training attention needs pivot_idx and no memory')
+            sep = SparseSpec(pivot_idx, self.query_window, self.key_window_times)
+        else:
+            sep = mask_to_sep(ltor_mask, sq, sk)
         mixed = _as_bf16(mixed)
         q = mixed[:, sk - sq:, :h]
         ctx = _AttnFn.apply(q, mixed[..., h:2 * h], mixed[..., 2 * h:], heads, sep)
@@ -312,7 +319,10 @@ class GPT2ParallelSelfAttention(torch.nn.Module):
 class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, heads, sep):
-        out, lse = ops.attn_fwd(q, k, v, heads, sep=sep, want_lse=True)
+        if isinstance(sep, SparseSpec):
+            out, lse = ops.attn_sparse_fwd(q, k, v, heads, sep.pivot_idx, sep.w, sep.times, want_lse=True)
+        else:
+            out, lse = ops.attn_fwd(q, k, v, heads, sep=sep, want_lse=True)
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.cfg = (heads, sep)
         return out
@@ -323,7 +333,11 @@ class _AttnFn(torch.autograd.Function):
         heads, sep = ctx.cfg
         if q.shape[1] != k.shape[1]:
             raise NotImplementedError('attention backward with memory (sq != sk) is not supported')
-        d_qkv = ops.attn_bwd(q, k, v, out, _as_bf16(d_out).contiguous(), lse, heads, sep=sep)
+        if isinstance(sep, SparseSpec):
+            d_qkv = ops.attn_sparse_bwd(q, k, v, out, _as_bf16(d_out).contiguous(), lse, heads, sep.pivot_idx, sep.w,
+                                        sep.times)
+        else:
+            d_qkv = ops.attn_bwd(q, k, v, out, _as_bf16(d_out).contiguous(), lse, heads, sep=sep)
         h = q.shape[2]
         return d_qkv[..., :h], d_qkv[..., h:2 * h], d_qkv[..., 2 * h:], None, None
 
@@ -406,13 +420,19 @@ class GPT2ParallelTransformerLayer(torch.nn.Module):
 
     def forward(self, hidden_states, ltor_mask, pivot_idx=None, is_sparse=0, mem=None):
         """Reference signature: hidden_states [b, s, h], mask [1,1,s,s] or int sep; `mem` = hidden-state memory
-        [b, t, h] (re-normalised and re-projected exactly like mpu/sparse_transformer.py:320, :136-141)."""
-        if is_sparse != 0:
-            raise NotImplementedError('sparse attention (is_sparse=%d) is not implemented in this round' % is_sparse)
+        [b, t, h] (re-normalised and re-projected exactly like mpu/sparse_transformer.py:320, :136-141).
+        is_sparse == 1: `ltor_mask` is the pivot_attention_mask of :569 (evaluated in closed form from pivot_idx)."""
+        if is_sparse not in (0, 1):
+            raise NotImplementedError('is_sparse=2 runs through GPT2ParallelTransformer (K|V cache + cv_attn_gather)')
         b, sq, h = hidden_states.shape
         x = hidden_states.reshape(b * sq, h).float().contiguous()
         am_x = ops.absmax(x)
-        if mem is None:
+        if is_sparse == 1:
+            if mem is not None or pivot_idx is None:
+                raise ValueError('sparse training attention needs pivot_idx and no memory')
+            att = self.attention
+            out, _ = self.fused_forward(x, am_x, b, sq, SparseSpec(pivot_idx, att.query_window, att.key_window_times))
+        elif mem is None:
             sep = mask_to_sep(ltor_mask, sq, sq)
             out, _ = self.fused_forward(x, am_x, b, sq, sep)
         else:
@@ -525,14 +545,18 @@ class GPT2ParallelTransformer(torch.nn.Module):
         num_pivot = max_text_num + int((left_boundary - max_text_num) * ratio)
         return window_idx, img_indices, txt_indices, num_pivot
 
-    def sample_pivots(self, window_idx, img_indices, txt_indices, num_pivot):
-        """Fresh pivots for one layer (:591-600): all text positions + a Python random.sample of image positions."""
-        pivot_idx = torch.stack([
+    @staticmethod
+    def sample_pivot_idx(img_indices, txt_indices, num_pivot):
+        """:557-565 / :591-599 — all text positions + a Python random.sample of image positions, per sequence."""
+        return torch.stack([
             torch.cat((text_idx,
                        img_indices[i][torch.tensor(random.sample(range(len(img_indices[i])), k=num_pivot - len(text_idx)),
                                                    dtype=torch.long, device=text_idx.device)]), dim=0)
             for i, text_idx in enumerate(txt_indices)])
-        return torch.cat((pivot_idx, window_idx), dim=-1)
+
+    def sample_pivots(self, window_idx, img_indices, txt_indices, num_pivot):
+        """Fresh pivots for one layer of sparse inference (:591-600) followed by the trailing window."""
+        return torch.cat((self.sample_pivot_idx(img_indices, txt_indices, num_pivot), window_idx), dim=-1)
 
     def run_layers(self, x, am_x, b, sq, sep, mems, word_embedding_weight=None, is_sparse=0, txt_indices_bool=None,
                    img_indices_bool=None):
@@ -555,9 +579,25 @@ class GPT2ParallelTransformer(torch.nn.Module):
             if sq > self.query_window * self.key_window_times:
                 raise ValueError('the fed tokens must fit in the attention window (query_window * key_window_times)')
             plan = self.sparse_index_plan(caches.t + sq, txt_indices_bool, img_indices_bool, b, x.device)
+        elif is_sparse == 1:
+            # sparse training (mpu/sparse_transformer.py:491-496, :556-589): fresh pivots for every checkpointed chunk
+            if mems:
+                raise NotImplementedError('sparse training attention takes no memory (:567 asserts the same)')
+            if not self.checkpoint_activations:
+                raise AssertionError('Please use checkpoint_activations for sparse attention training.')   # :586
+            if sq % self.query_window != 0:
+                raise ValueError('The seq_len must be exactly divided by window_size.')                       # :713
+            img_all = [img_indices_bool[i][:sq].nonzero(as_tuple=False).view(-1) for i in range(b)]
+            txt_all = [txt_indices_bool[i][:sq].nonzero(as_tuple=False).view(-1) for i in range(b)]
         elif is_sparse != 0:
-            raise NotImplementedError('sparse training (is_sparse=1) is not implemented in this round')
+            raise ValueError('is_sparse must be 0, 1 or 2')
+        spec = None
         for i, layer in enumerate(self.layers):
+            if is_sparse == 1 and i % max(1, self.checkpoint_num_layers) == 0:
+                spec = SparseSpec(self.sample_pivot_idx(img_all, txt_all, self.num_pivot), self.query_window,
+                                  self.key_window_times)
+            if spec is not None:
+                sep = spec
             if mode == 'kv' and plan is not None:
                 pw_idx = self.sample_pivots(*plan)
                 cache_i, t_all, heads = caches.buf[i], caches.t + sq, self.num_attention_heads
@@ -571,7 +611,7 @@ class GPT2ParallelTransformer(torch.nn.Module):
                 out = layer(x.view(b, sq, h), sep, mem=mems[i]).view(b * sq, h)
                 am_x = ops.absmax(out)
             elif self.checkpoint_activations and torch.is_grad_enabled() and x.requires_grad:
-                def run(x_, am_, layer=layer):
+                def run(x_, am_, layer=layer, sep=sep):      # `sep` bound now: the recomputation runs in the backward
                     return layer.fused_forward(x_, am_, b, sq, sep)
                 out, am_x = checkpoint(run, x, am_x)
             else:
@@ -597,11 +637,9 @@ class GPT2ParallelTransformer(torch.nn.Module):
                 *mems):
         """Reference signature (mpu/sparse_transformer.py:471): hidden_states = word embeddings [b, s, h].
         Returns (final-LN output [b, s, h], *mems)."""
-        if is_sparse == 1:
-            raise NotImplementedError('sparse training (is_sparse=1) is not implemented in this round')
         b, sq, h = hidden_states.shape
         mem_len = mems[0].size(1) if mems else 0
-        sep = 0 if is_sparse == 2 else mask_to_sep(attention_mask, sq, sq + mem_len)
+        sep = 0 if is_sparse != 0 else mask_to_sep(attention_mask, sq, sq + mem_len)
         pe = torch.nn.functional.embedding(position_ids, self.position_embeddings.weight)
         x = (hidden_states.float() + pe.float()).reshape(b * sq, h).contiguous()
         if self.training and self.embedding_dropout_prob > 0:
@@ -645,9 +683,21 @@ class _FinalLNFn(torch.autograd.Function):
         return dx, None, dg.to(ctx.meta[0]), db.to(ctx.meta[1]), None
 
 
-def sparse_attention(*args, **kwargs):
-    """mpu/sparse_transformer.py:675-725 — not implemented in this round."""
-    raise NotImplementedError('sparse_attention is not implemented in this round')
+def sparse_attention(q, k, v, pivot_idx, pivot_attention_mask=None, query_window=128, key_window_times=6,
+                     attention_dropout=None):
+    """mpu/sparse_transformer.py:675-725 on [b, np, s, hn] tensors (API parity; the model path reads the packed QKV
+    GEMM output in place).  `pivot_attention_mask` is accepted for signature parity: the kernel evaluates the mask the
+    reference builds (rmask of :491-496 gathered at pivot_idx, :569) in closed form — pivot p is visible to query i
+    iff pivot_idx[p] < band_start(i)."""
+    if attention_dropout is not None and attention_dropout.training and attention_dropout.p > 0:
+        raise NotImplementedError('attention-probability dropout is not available with sparse training attention')
+    b, nh, s, hn = q.shape
+
+    def tok_major(t):
+        return _as_bf16(t).permute(0, 2, 1, 3).reshape(b, t.shape[2], nh * hn).contiguous()
+
+    ctx = _AttnFn.apply(tok_major(q), tok_major(k), tok_major(v), nh, SparseSpec(pivot_idx, query_window, key_window_times))
+    return ctx.view(b, s, nh, hn).permute(0, 2, 1, 3).to(q.dtype)
 
 
 def sparse_attention_inference(q, k, v, pivot_and_window_idx, **kwargs):

@@ -176,6 +176,42 @@ def attn_bwd(q, k, v, out, d_out, lse, heads, *, sep=0, dropout_p=0.0, drop_mask
     return dqkv
 
 
+def attn_sparse_fwd(q, k, v, heads, pivot_idx, query_window, key_window_times, *, want_lse=False):
+    """Sparse TRAINING attention (mpu/sparse_transformer.py:675-725): q, k, v [b, s, heads*64] bf16 views,
+    pivot_idx int64 [b, n_piv].  Returns ctx [b, s, heads*64] bf16 (and lse [b, heads, s] fp32)."""
+    require_cuda(q, k, v, pivot_idx)
+    b, s, h = q.shape
+    n_piv = pivot_idx.shape[1]
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1 and h == heads * 64
+    assert pivot_idx.dtype == torch.int64 and pivot_idx.shape[0] == b
+    pivot_idx = pivot_idx.contiguous()
+    out = torch.empty((b, s, h), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((b, heads, s), dtype=torch.float32, device=q.device) if want_lse else None
+    ws = torch.empty(lib().cv_attn_sparse_workspace_bytes(b, heads, 64, n_piv), dtype=torch.uint8, device=q.device)
+    rc = lib().cv_attn_sparse_fwd(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
+                                  v.stride(0), ptr(pivot_idx), ptr(out), out.stride(1), out.stride(0), ptr(lse), ptr(ws),
+                                  b, heads, 64, s, n_piv, int(query_window), int(key_window_times), stream_ptr())
+    check(rc, "cv_attn_sparse_fwd")
+    return (out, lse) if want_lse else out
+
+
+def attn_sparse_bwd(q, k, v, out, d_out, lse, heads, pivot_idx, query_window, key_window_times):
+    """Backward of attn_sparse_fwd.  Returns dqkv [b, s, 3*heads*64] bf16 (dQ | dK | dV)."""
+    require_cuda(q, k, v, out, d_out, lse, pivot_idx)
+    b, s, h = q.shape
+    n_piv = pivot_idx.shape[1]
+    assert out.is_contiguous() and d_out.is_contiguous() and d_out.dtype == torch.bfloat16
+    pivot_idx = pivot_idx.contiguous()
+    dqkv = torch.empty((b, s, 3 * h), dtype=torch.bfloat16, device=q.device)
+    ws = torch.empty(lib().cv_attn_sparse_bwd_workspace_bytes(b, heads, 64, s, n_piv), dtype=torch.uint8,
+                     device=q.device)
+    rc = lib().cv_attn_sparse_bwd(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
+                                  v.stride(0), ptr(pivot_idx), ptr(out), ptr(d_out), ptr(lse), ptr(dqkv), ptr(ws), b,
+                                  heads, 64, s, n_piv, int(query_window), int(key_window_times), stream_ptr())
+    check(rc, "cv_attn_sparse_bwd")
+    return dqkv
+
+
 # ----------------------------------------------------------------------------------------------------
 # embedding, cross-entropy, small backward helpers
 # ----------------------------------------------------------------------------------------------------
@@ -311,7 +347,7 @@ def decode_step_workspace(hidden, heads, device):
 
 
 def decode_step(layer_table, num_layers, heads, eps, eps_final, wte, wpe, lnf_g, lnf_b, ids, pos, cur_len, cache,
-                logits, workspace):
+                logits, workspace, prof=None):
     """One token per sequence through every layer + logits in ONE kernel (cv_decode_step).
     layer_table: int64 [num_layers, 16] device tensor of parameter pointers in cv_decode_layer order;
     cache: [L, b, max_len, 2h] bf16; ids/pos: int64 [b(,1)]; cur_len: int32 [1]; logits: fp32 [b, V] (written)."""
@@ -328,7 +364,7 @@ def decode_step(layer_table, num_layers, heads, eps, eps_final, wte, wpe, lnf_g,
         max_len=max_len, eps=float(eps), eps_final=float(eps_final), wte=ptr(wte), wpe=ptr(wpe), lnf_g=ptr(lnf_g),
         lnf_b=ptr(lnf_b), ids=ptr(ids), pos=ptr(pos), cur_len=ptr(cur_len), cache=ptr(cache),
         cache_layer_stride=cache.stride(0), cache_batch_stride=cache.stride(1), logits=ptr(logits),
-        ld_logits=logits.stride(0), workspace=ptr(workspace))
+        ld_logits=logits.stride(0), workspace=ptr(workspace), prof=ptr(prof))
     import ctypes
     check(lib().cv_decode_step(ctypes.byref(a), stream_ptr()), "cv_decode_step")
     return logits

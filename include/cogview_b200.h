@@ -140,6 +140,28 @@ int64_t cv_colsum_workspace_bytes(int cols);
 int cv_colsum_bf16(const void* dy, int64_t ld, void* out, float* workspace, int rows, int cols, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Sparse TRAINING attention: sparse_attention + _chunk (mpu/sparse_transformer.py:675-725, :629-650) with the
+ * pivot mask of :491-496 / :569 in closed form.  One softmax over
+ *     band   : keys j with band_start(i) <= j <= i,  band_start(i) = max(0, i / w - times + 1) * w
+ *     pivots : the n_piv gathered keys K[pivot_idx], V[pivot_idx] whose position is < band_start(i), scores + log(s / n_piv)
+ * walked by ONE flash kernel as band tiles followed by gathered-pivot tiles (tcgen05 + TMA, same kernel as cv_attn_fwd);
+ * masked entries carry exactly -10000 as in the reference.  q / k / v: [b, s, heads*64] bf16 views as for cv_attn_fwd;
+ * pivot_idx: int64 [b, n_piv] (distinct positions per sequence, mpu/sparse_transformer.py:557-565); s % w == 0.
+ * The backward runs the band pass and the pivot pass with the joint lse / delta, scatters the pivot dK / dV back and
+ * writes dqkv [b, s, 3*heads*64] (dQ | dK | dV).  Attention-probability dropout is not available in this mode.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t cv_attn_sparse_workspace_bytes(int b, int heads, int head_dim, int n_piv);
+int cv_attn_sparse_fwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
+                       int64_t ldv, int64_t bsv, const int64_t* pivot_idx, void* out, int64_t ldo, int64_t bso,
+                       float* lse, void* workspace, int b, int heads, int head_dim, int s, int n_piv, int query_window,
+                       int key_window_times, void* stream);
+int64_t cv_attn_sparse_bwd_workspace_bytes(int b, int heads, int head_dim, int s, int n_piv);
+int cv_attn_sparse_bwd(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
+                       int64_t ldv, int64_t bsv, const int64_t* pivot_idx, const void* out, const void* d_out,
+                       const float* lse, void* dqkv, void* workspace, int b, int heads, int head_dim, int s, int n_piv,
+                       int query_window, int key_window_times, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Decode (one new token per sequence): HBM-bound weight streaming, CUDA cores.
  *   cv_linear_small_m: y[M,N] = x[M,K] W[N,K]^T + bias (+GELU) (+abs-max), 1 <= M <= 16 — F.linear of
  *     mpu/layers.py:243,319 and the last-token logits GEMM (model/gpt2_modeling.py:117) inside the sampling
@@ -204,6 +226,8 @@ typedef struct cv_decode_step_args {
     float* logits;
     int64_t ld_logits;
     void* workspace;
+    void* prof;   /* NULL, or uint64 [SMs][num_layers][16]: %globaltimer stamps of the 13 phase boundaries of every
+                     layer, per CTA (tools/step_prof.py) */
 } cv_decode_step_args;               /* HOST struct */
 int64_t cv_decode_step_workspace_bytes(int hidden, int heads);
 int cv_decode_step(const cv_decode_step_args* args, void* stream);

@@ -190,6 +190,33 @@ def vqvae_golden(ref):
                         recon=rec.numpy(), min_gap=np.float32(gap.min().item()))
 
 
+def vqvae_golden_256(ref, n=17):
+    """configs[3] shapes: 256x256 images, 512-channel maps, 32x32 codes, more images than one batch chunk (16).
+    Stored: codes, the reference's nearest / second-nearest distance gap per code (which codes are decisive for a
+    bf16 encoder), strided samples of z and of the reconstruction."""
+    print("VQ-VAE 256x256: reference outputs for %d images" % n)
+    sd = recipes.vqvae_state_dict(seed=0)
+    model = ref["vq_api"].new_model()
+    model.load_state_dict(sd)
+    model.eval()
+    img = recipes.images(n, size=256, seed=5)
+    with torch.no_grad():
+        z_ref = model.enc_b(img)                                   # [n, 32, 32, 256]
+        codes = ref["vq_api"].img2code(model, img)                 # [n, 1024]
+        rec = ref["vq_api"].code2img(model, codes.view(n, 32, 32))
+        o_codes = O.img2code(sd, img)
+        assert torch.equal(o_codes, codes), "oracle codes differ from the reference at 256x256"
+        close(O.code2img(sd, codes.view(n, 32, 32)), rec, 2e-5, "decoded 256x256 image")
+        d = O.vq_distances(z_ref.reshape(-1, 256), sd['quantize_t.embed'])
+        top2 = torch.topk(-d, 2, dim=1).values
+        gap = (top2[:, 0] - top2[:, 1]).view(n, 1024)
+    print("  gap: min %.3e median %.3e; z scale %.3f" % (gap.min(), gap.median(), z_ref.abs().max()))
+    np.savez_compressed(os.path.join(GOLD, "vqvae_256.npz"), codes=codes.numpy().astype(np.int16),
+                        gap=gap.numpy().astype(np.float32), z_strided=z_ref[:, ::8, ::8, :].numpy(),
+                        z_absmax=np.float32(z_ref.abs().max().item()),
+                        recon_strided=rec[:, :, ::16, ::16].numpy(), recon_absmax=np.float32(rec.abs().max().item()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -197,6 +224,7 @@ def main():
     gpt2_golden(ref)
     attention_golden(ref)
     vqvae_golden(ref)
+    vqvae_golden_256(ref)
     print("golden fixtures written to", GOLD)
 
 

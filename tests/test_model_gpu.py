@@ -226,3 +226,47 @@ def test_filling_sequence_graph_sampling_matches_eager_loop(monkeypatch):
     sampled, _ = _fill(monkeypatch, True, 200, 1)
     assert sampled.shape == (3, n) and int(sampled[:, 21:].min()) >= 0 and int(sampled[:, 21:].max()) < recipes.IMG_VOCAB
     assert len({tuple(r.tolist()) for r in sampled[:, 21:]}) > 1          # beams diverge
+
+
+def test_4b_shaped_layer_forward_backward_matches_oracle():
+    """One CogView-base layer at its BASELINE shape (h = 2560, 40 heads, s = 1088 tokens, b = 1) through GPT2Model:
+    logits, loss and every gradient against the fp32 oracle on the same (bf16-rounded) weights.  The vocabulary is cut
+    to 2048 rows so that the CPU oracle finishes in seconds; every other dimension is the 4B model's."""
+    from cogview_b200 import mpu
+    from cogview_b200.model import GPT2Model
+    cfg = dict(num_layers=1, vocab_size=2048, hidden_size=2560, num_attention_heads=40, max_sequence_length=1088)
+    s = 1088
+    sd32 = recipes.gpt2_state_dict(seed=11, **cfg)
+    m = GPT2Model(num_layers=1, vocab_size=cfg["vocab_size"], hidden_size=cfg["hidden_size"],
+                  num_attention_heads=cfg["num_attention_heads"], embedding_dropout_prob=0.0,
+                  attention_dropout_prob=0.0, output_dropout_prob=0.0, max_sequence_length=s, max_memory_length=0,
+                  checkpoint_activations=False)
+    m.load_state_dict(sd32)
+    m = m.cuda().bfloat16().train()
+    g = torch.Generator().manual_seed(5)
+    tokens = torch.randint(0, cfg["vocab_size"], (1, s), generator=g)
+    labels = torch.randint(0, cfg["vocab_size"], (1, s), generator=g)
+    pos = torch.arange(s).unsqueeze(0)
+    logits, *_ = m(tokens.cuda(), pos.cuda(), torch.tril(torch.ones((1, 1, s, s), device="cuda")), None, None, 0)
+    losses = mpu.vocab_parallel_cross_entropy(logits.contiguous().float(), labels.cuda())
+    loss = losses.mean()
+    loss.backward()
+    sdr = {k: v.to(torch.bfloat16).float().requires_grad_(True) for k, v in sd32.items()}
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
+    o_logits, _ = O.gpt2_forward(sdr, cfg["num_attention_heads"], tokens, pos, torch.tril(torch.ones((1, 1, s, s))))
+    o_losses = O.vocab_parallel_cross_entropy(o_logits, labels)
+    o_loss = o_losses.mean()
+    o_loss.backward()
+    scale = o_logits.abs().max().item()
+    err = (logits.float().cpu() - o_logits.detach()).abs().max().item()
+    print("4B layer: logits max|diff| %.3e (scale %.3e), loss %.5f vs %.5f" % (err, scale, loss.item(), o_loss.item()))
+    assert err < 2e-2 * scale
+    assert abs(loss.item() - o_loss.item()) < 1e-2
+    worst = ("", 0.0)
+    for n, p in m.named_parameters():
+        ref = sdr[n].grad
+        e = ((p.grad.float().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+        if e > worst[1]:
+            worst = (n, e)
+        assert e < 6e-2, (n, e)
+    print("4B layer: worst relative gradient error %s %.3e" % worst)

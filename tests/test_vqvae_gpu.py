@@ -108,3 +108,36 @@ def test_conv_kernels_match_torch_on_larger_maps(setup):
     yt = ops.conv_transpose2d_k4s2(xs.permute(0, 2, 3, 1).contiguous().cuda(), _pack_convT(wt.to(torch.bfloat16)).cuda(),
                                    bb.cuda(), relu=False)
     assert ((yt.float().cpu().permute(0, 3, 1, 2) - ref_t).abs().max() / ref_t.abs().max()).item() < 1e-2
+
+
+def test_configs3_shapes_256x256_against_reference_fixture(setup, golden_dir):
+    """BASELINE configs[3] shapes — 256x256 images, 512-channel maps, 32x32 codes, 17 images (more than one
+    batch chunk of 16) — against tests/golden/vqvae_256.npz, written by oracle/make_golden.py from the unmodified
+    reference.  Contract: z within 2e-2 of its scale; codes EQUAL wherever the reference's nearest / second-nearest
+    distance gap exceeds the bound the bf16 encoder error puts on a distance (2 |dz| |e_i - e_j| <= 4 |dz| max|e|),
+    overall agreement reported; the decoder on the reference's codes within 3e-2 of the image scale."""
+    m, vq = setup["model"], setup["vqvae"]
+    g = np.load(os.path.join(golden_dir, "vqvae_256.npz"))
+    n = g["codes"].shape[0]
+    img = recipes.images(n, size=256, seed=5).cuda()
+    with torch.no_grad():
+        z = m.enc_b(img).float().cpu()
+        codes = vq.img2code(m, img).cpu().numpy().reshape(n, 1024)
+    zs = torch.from_numpy(g["z_strided"])
+    dz = (z[:, ::8, ::8, :] - zs).abs().max().item()
+    print("256x256: encoder |dz| max %.3e (z scale %.3f)" % (dz, float(g["z_absmax"])))
+    assert dz < 2e-2 * float(g["z_absmax"])
+    ref_codes = g["codes"].astype(np.int64)
+    agree = (codes == ref_codes)
+    emax = setup["sd"]["quantize_t.embed"].abs().sum(0).max().item()      # bound on |<dz, e_i - e_j>| / |dz|_inf / 2
+    decisive = g["gap"] > 4.0 * dz * emax
+    print("256x256: code agreement %.4f (%d of %d); decisive codes %d, all equal: %s" % (
+        agree.mean(), agree.sum(), agree.size, decisive.sum(), bool(agree[decisive].all())))
+    assert agree[decisive].all()
+    assert agree.mean() > 0.97
+    with torch.no_grad():
+        rec = vq.code2img(m, torch.from_numpy(ref_codes).view(n, 32, 32).cuda()).cpu()
+    rr = torch.from_numpy(g["recon_strided"])
+    err = (rec[:, :, ::16, ::16] - rr).abs().max().item()
+    print("256x256: decoder max abs err %.3e (image scale %.2f)" % (err, float(g["recon_absmax"])))
+    assert rec.shape == (n, 3, 256, 256) and err < 3e-2 * float(g["recon_absmax"])
