@@ -556,7 +556,8 @@ class GPT2ParallelTransformer(torch.nn.Module):
 
     def sample_pivots(self, window_idx, img_indices, txt_indices, num_pivot):
         """Fresh pivots for one layer of sparse inference (:591-600) followed by the trailing window."""
-        return torch.cat((self.sample_pivot_idx(img_indices, txt_indices, num_pivot), window_idx), dim=-1)
+        return torch.cat((GPT2ParallelTransformer.sample_pivot_idx(img_indices, txt_indices, num_pivot), window_idx),
+                         dim=-1)
 
     def run_layers(self, x, am_x, b, sq, sep, mems, word_embedding_weight=None, is_sparse=0, txt_indices_bool=None,
                    img_indices_bool=None):
