@@ -49,7 +49,6 @@ constexpr int TILE = 16;            // weight rows (output columns) per MMA tile
 constexpr int KG = 4;               // K groups of the 4h->h matrix
 constexpr int HD = 64;              // head dim
 constexpr int MAXST = 8;            // ring stages (upper bound)
-constexpr int NV = 2;               // 4-column vectors per thread and row in the glue: h <= 4 * CT * NV = 4096
 constexpr int MAXM = 8;
 constexpr int AUNR = 4;             // attention: 4-key groups in flight per warp iteration (16 keys)
 constexpr int PART_STRIDE = HD + 2; // attention partial: acc[64], m, l
@@ -80,7 +79,7 @@ struct Params {
 // shared-memory carve-up (bytes from the 1024-aligned base)
 constexpr int SM_BAR = 0;                                  // full[MAXST], empty[MAXST]
 constexpr int SM_FLAG = 2 * MAXST * 8;                     // int flags
-constexpr int SM_RED = 256;                                // float red[4][CW][MAXM + 1]
+constexpr int SM_RED = 256;                                // float2 red[4][CW] (fits the [4][CW][MAXM + 1] slot)
 constexpr int SM_PART = SM_RED + 4 * CW * (MAXM + 1) * 4;  // float part[2][CW][TILE][8]
 constexpr int SM_XOP = ((SM_PART + 2 * CW * TILE * 8 * 4) + 127) / 128 * 128;
 
@@ -196,19 +195,29 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 }
             }
         };
-        for (int l = 0; l < p.L; ++l) {
-            const cv_decode_layer& Lw = p.layers[l];
-            produce(make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0));
-            produce(make_mat(Lw.w_dense, h, h, cta, G, 0));
-            produce(make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0));
-            produce(make_mat(Lw.w_fc2, 4 * (int64_t)h, h, cta / KG, G / KG, (cta % KG) * h));
+        for (int it = 0; it <= 4 * p.L; ++it) {       // one call site (instruction-cache footprint)
+            const int l = it >> 2, which = it & 3;
+            Mat m;
+            if (it == 4 * p.L) {
+                m = make_mat(p.wte, h, p.V, cta, G, 0);
+            } else {
+                const cv_decode_layer& Lw = p.layers[l];
+                if (which == 0) m = make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0);
+                else if (which == 1) m = make_mat(Lw.w_dense, h, h, cta, G, 0);
+                else if (which == 2) m = make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0);
+                else m = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, cta / KG, G / KG, (cta % KG) * h);
+            }
+            produce(m);
         }
-        produce(make_mat(p.wte, h, p.V, cta, G, 0));
         return;
     }
 
     // ============================================================================================
     // consumer warps
+    //
+    // Every heavy routine below has exactly ONE call site, inside a phase loop: inlined copies of straight-line
+    // code made the first version of this kernel 240 KB of SASS and instruction-cache bound (ncu: 64 % I-cache
+    // hit rate, 17 % of the stall samples "no instruction"); one layer's working set now stays cache resident.
     // ============================================================================================
     const int g = lane >> 2, q = lane & 3;
     const int kpw = p.kstage / GW;                 // k elements per warp and stage ( = 32 * CPW )
@@ -320,188 +329,148 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
     // Sandwich-LN glue, computed redundantly by every CTA:
     //   v  = res + LN_post(gemm_out / (max|gemm_out| / 8))          (skipped when gemm_out == nullptr)
     //   xn = LN_pre(v / (max|v| / 8))  -> shared-memory operand;   v -> res_out (this CTA's column slice only)
-    // res = res_in (fp32, L2) or, when res_in == nullptr, the embedding wte[ids] + wpe[pos].
-    // A thread owns the 4-column vectors tid + 256 j of every row (8-byte bf16 / 16-byte fp32 accesses); the phase is
-    // bound by instruction issue (2 warps per scheduler), so the code is kept to ~12 instructions per element.
-    int prof_layer = -1;       // >= 0: sub-stamps of the glue go to slots 13..15 of this layer
-    auto glue = [&](auto emb_tag, const bf16* gemm_out, const bf16* g_post, const bf16* b_post, float eps_post,
-                    const float* res_in, float* res_out, const bf16* g_pre, const bf16* b_pre, float eps_pre) {
-        constexpr bool EMB = decltype(emb_tag)::value;      // residual = embedding of the new token (layer 0)
+    // res = res_in (fp32, L2) or, when EMB, the embedding wte[ids] + wpe[pos] of the new token.
+    // Thread mapping: row = tid / TPR (TPR = 512 / MR threads per sequence), NVT 4-column vectors per thread — every
+    // thread works on ONE row, so a row statistic is a 1-value warp reduction + WPR partials through shared memory.
+    constexpr int TPR = CT / MR;
+    constexpr int WPR = TPR / 32;
+    constexpr int NVT = (2560 / 4 + TPR - 1) / TPR;
+    struct GlueArgs {
+        const bf16 *gemm_out, *g_post, *b_post;
+        const float* res_in;
+        float* res_out;
+        const bf16 *g_pre, *b_pre;
+        float eps_post, eps_pre;
+        int prof_layer;
+    };
+    auto glue = [&](auto emb_tag, const GlueArgs& a) {
+        constexpr bool EMB = decltype(emb_tag)::value;
         const int hv = h >> 2;
         const float inv_h = 1.0f / h;
-        bool ok[NV];
-        uint2 gq[NV], bq[NV];
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int vi = tid + CT * j;
-            ok[j] = vi < hv;
-            gq[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(g_pre) + vi) : make_uint2(0u, 0u);
-            bq[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(b_pre) + vi) : make_uint2(0u, 0u);
-        }
-        const uint2* wrow[EMB ? MR : 1];
-        const uint2* prow[EMB ? MR : 1];
-        if (EMB) {
-#pragma unroll
-            for (int mi = 0; mi < MR; ++mi) {
-                const int mc = mi < M ? mi : 0;
-                wrow[EMB ? mi : 0] = reinterpret_cast<const uint2*>(p.wte + (size_t)__ldg(p.ids + mc) * h);
-                prow[EMB ? mi : 0] = reinterpret_cast<const uint2*>(p.wpe + (size_t)__ldg(p.pos + mc) * h);
-            }
-        }
-        auto residual = [&](int mi, int vi) -> float4 {
-            if (!EMB) return __ldcg(reinterpret_cast<const float4*>(res_in) + mi * hv + vi);
-            const uint2 a = __ldg(wrow[EMB ? mi : 0] + vi);
-            const uint2 b = __ldg(prow[EMB ? mi : 0] + vi);
-            return make_float4(bflo(a.x) + bflo(b.x), bfhi(a.x) + bfhi(b.x), bflo(a.y) + bflo(b.y), bfhi(a.y) + bfhi(b.y));
-        };
-        // block-wide: s[m] <- sum over the row, mx <- max over everything; one named barrier
-        auto reduce = [&](float (&s)[MR], float& mx, int which) {
-#pragma unroll
-            for (int mi = 0; mi < MR; ++mi) s[mi] = warp_sum(s[mi]);
+        const int grow = tid / TPR, gt = tid - grow * TPR;
+        const bool row_ok = grow < M;
+        float2* red2 = reinterpret_cast<float2*>(red);       // [4][CW] (sum, max)
+        auto reduce = [&](float& s, float& mx, int which) {
+            s = warp_sum(s);
             mx = warp_max(mx);
-            float* rw = red + (which * CW + warp) * (MAXM + 1);
-            if (lane == 0) {
-#pragma unroll
-                for (int mi = 0; mi < MR; ++mi) rw[mi] = s[mi];
-                rw[MAXM] = mx;
-            }
+            if (lane == 0) red2[which * CW + warp] = make_float2(s, mx);
             named_bar_sync(1, CT);
+            float t = 0.f, m2 = 0.f;
 #pragma unroll
-            for (int mi = 0; mi < MR; ++mi) {
-                float t = 0.f;
+            for (int w = 0; w < WPR; ++w) t += red2[which * CW + grow * WPR + w].x;
 #pragma unroll
-                for (int w = 0; w < CW; ++w) t += red[(which * CW + w) * (MAXM + 1) + mi];
-                s[mi] = t;
-            }
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < CW; ++w) t = fmaxf(t, red[(which * CW + w) * (MAXM + 1) + MAXM]);
-            mx = t;
+            for (int w = 0; w < CW; ++w) m2 = fmaxf(m2, red2[which * CW + w].y);
+            s = t;
+            mx = m2;
         };
-        auto sum4 = [](const float4& a) { return (a.x + a.y) + (a.z + a.w); };
-        auto amax4 = [](const float4& a) { return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))); };
-        auto dev4 = [](const float4& a, float mean) {
-            const float x = a.x - mean, y = a.y - mean, z = a.z - mean, w = a.w - mean;
-            return (x * x + y * y) + (z * z + w * w);
+        auto sum4 = [](const float4& x) { return (x.x + x.y) + (x.z + x.w); };
+        auto amax4 = [](const float4& x) { return fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))); };
+        auto dev4 = [](const float4& x, float mean) {
+            const float a0 = x.x - mean, a1 = x.y - mean, a2 = x.z - mean, a3 = x.w - mean;
+            return (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
         };
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint2* wrow = nullptr;
+        const uint2* prow = nullptr;
+        if (EMB && row_ok) {
+            wrow = reinterpret_cast<const uint2*>(p.wte + (size_t)__ldg(p.ids + grow) * h);
+            prow = reinterpret_cast<const uint2*>(p.wpe + (size_t)__ldg(p.pos + grow) * h);
+        }
+        auto residual = [&](int vi) -> float4 {
+            if (!EMB) return __ldcg(reinterpret_cast<const float4*>(a.res_in) + grow * hv + vi);
+            const uint2 x = __ldg(wrow + vi), y = __ldg(prow + vi);
+            return make_float4(bflo(x.x) + bflo(y.x), bfhi(x.x) + bfhi(y.x), bflo(x.y) + bflo(y.y), bfhi(x.y) + bfhi(y.y));
+        };
 
-        float4 v[MR][NV];
-        if (gemm_out != nullptr) {
-            uint2 gp[NV], bp[NV];
+        float4 v[NVT];
+        if (a.gemm_out != nullptr) {
+            float s = 0.f, amax = 0.f;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const int vi = tid + CT * j;
-                gp[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(g_post) + vi) : make_uint2(0u, 0u);
-                bp[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(b_post) + vi) : make_uint2(0u, 0u);
-            }
-            float s[MR], amax = 0.f;
-#pragma unroll
-            for (int mi = 0; mi < MR; ++mi) {
-                s[mi] = 0.f;
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    uint2 u = make_uint2(0u, 0u);
-                    if (mi < M && ok[j]) u = __ldcg(reinterpret_cast<const uint2*>(gemm_out) + mi * hv + tid + CT * j);
-                    v[mi][j] = make_float4(bflo(u.x), bfhi(u.x), bflo(u.y), bfhi(u.y));
-                    s[mi] += sum4(v[mi][j]);
-                    amax = fmaxf(amax, amax4(v[mi][j]));
-                }
+            for (int j = 0; j < NVT; ++j) {
+                const int vi = gt + TPR * j;
+                uint2 u = make_uint2(0u, 0u);
+                if (row_ok && vi < hv) u = __ldcg(reinterpret_cast<const uint2*>(a.gemm_out) + grow * hv + vi);
+                v[j] = make_float4(bflo(u.x), bfhi(u.x), bflo(u.y), bfhi(u.y));
+                s += sum4(v[j]);
+                amax = fmaxf(amax, amax4(v[j]));
             }
             constexpr bool PRE = MR <= 4;               // small batches: the residual is fetched under the first reduction
-            float4 rs[PRE ? MR : 1][NV];
+            float4 rs[PRE ? NVT : 1];
             if (PRE) {
 #pragma unroll
-                for (int mi = 0; mi < MR; ++mi)
-#pragma unroll
-                    for (int j = 0; j < NV; ++j)
-                        rs[PRE ? mi : 0][j] = (mi < M && ok[j]) ? residual(mi, tid + CT * j) : zero4;
+                for (int j = 0; j < NVT; ++j) {
+                    const int vi = gt + TPR * j;
+                    rs[PRE ? j : 0] = (row_ok && vi < hv) ? residual(vi) : zero4;
+                }
             }
             reduce(s, amax, 0);
-            if (prof_layer >= 0) stamp(prof_layer, 13);
-            const float c = amax * 0.125f;
-            float ss[MR], dummy = 0.f;
+            if (a.prof_layer >= 0) stamp(a.prof_layer, 13);
+            const float c = amax * 0.125f, mean = s * inv_h;
+            float ss = 0.f, dummy = 0.f;
 #pragma unroll
-            for (int mi = 0; mi < MR; ++mi) {
-                const float mean = s[mi] * inv_h;
-                ss[mi] = 0.f;
-#pragma unroll
-                for (int j = 0; j < NV; ++j)
-                    if (ok[j]) ss[mi] += dev4(v[mi][j], mean);
-            }
+            for (int j = 0; j < NVT; ++j)
+                if (gt + TPR * j < hv) ss += dev4(v[j], mean);
             reduce(ss, dummy, 1);
+            const float rstd = rsqrtf(ss * inv_h + a.eps_post * c * c);
 #pragma unroll
-            for (int mi = 0; mi < MR; ++mi) {
-                const float mean = s[mi] * inv_h;
-                const float rstd = rsqrtf(ss[mi] * inv_h + eps_post * c * c);
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    float4& a = v[mi][j];
-                    const float4 r = PRE ? rs[PRE ? mi : 0][j] : ((mi < M && ok[j]) ? residual(mi, tid + CT * j) : zero4);
-                    a.x = (a.x - mean) * rstd * bflo(gp[j].x) + bflo(bp[j].x) + r.x;
-                    a.y = (a.y - mean) * rstd * bfhi(gp[j].x) + bfhi(bp[j].x) + r.y;
-                    a.z = (a.z - mean) * rstd * bflo(gp[j].y) + bflo(bp[j].y) + r.z;
-                    a.w = (a.w - mean) * rstd * bfhi(gp[j].y) + bfhi(bp[j].y) + r.w;
+            for (int j = 0; j < NVT; ++j) {
+                const int vi = gt + TPR * j;
+                if (row_ok && vi < hv) {
+                    const uint2 gp = __ldg(reinterpret_cast<const uint2*>(a.g_post) + vi);
+                    const uint2 bp = __ldg(reinterpret_cast<const uint2*>(a.b_post) + vi);
+                    const float4 r = PRE ? rs[PRE ? j : 0] : residual(vi);
+                    float4& x = v[j];
+                    x.x = (x.x - mean) * rstd * bflo(gp.x) + bflo(bp.x) + r.x;
+                    x.y = (x.y - mean) * rstd * bfhi(gp.x) + bfhi(bp.x) + r.y;
+                    x.z = (x.z - mean) * rstd * bflo(gp.y) + bflo(bp.y) + r.z;
+                    x.w = (x.w - mean) * rstd * bfhi(gp.y) + bfhi(bp.y) + r.w;
+                } else {
+                    v[j] = zero4;
                 }
             }
         } else {
 #pragma unroll
-            for (int mi = 0; mi < MR; ++mi)
-#pragma unroll
-                for (int j = 0; j < NV; ++j) v[mi][j] = (mi < M && ok[j]) ? residual(mi, tid + CT * j) : zero4;
+            for (int j = 0; j < NVT; ++j) {
+                const int vi = gt + TPR * j;
+                v[j] = (row_ok && vi < hv) ? residual(vi) : zero4;
+            }
         }
         // residual stream out (owner slice), statistics of v
         const int v_lo = (int)(((int64_t)hv * cta) / G), v_hi = (int)(((int64_t)hv * (cta + 1)) / G);
-        float s2[MR], amax2 = 0.f;
+        float s2 = 0.f, amax2 = 0.f;
 #pragma unroll
-        for (int mi = 0; mi < MR; ++mi) {
-            s2[mi] = 0.f;
-            if (mi < M) {
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    const int vi = tid + CT * j;
-                    if (ok[j]) {
-                        if (res_out != nullptr && vi >= v_lo && vi < v_hi)
-                            *(reinterpret_cast<float4*>(res_out) + mi * hv + vi) = v[mi][j];
-                        s2[mi] += sum4(v[mi][j]);
-                        amax2 = fmaxf(amax2, amax4(v[mi][j]));
-                    }
-                }
+        for (int j = 0; j < NVT; ++j) {
+            const int vi = gt + TPR * j;
+            if (row_ok && vi < hv) {
+                if (a.res_out != nullptr && vi >= v_lo && vi < v_hi)
+                    *(reinterpret_cast<float4*>(a.res_out) + grow * hv + vi) = v[j];
+                s2 += sum4(v[j]);
+                amax2 = fmaxf(amax2, amax4(v[j]));
             }
         }
         reduce(s2, amax2, 2);
-        if (prof_layer >= 0) stamp(prof_layer, 14);
-        const float c2 = amax2 * 0.125f;
-        float ss2[MR], dummy2 = 0.f;
+        if (a.prof_layer >= 0) stamp(a.prof_layer, 14);
+        const float c2 = amax2 * 0.125f, mean2 = s2 * inv_h;
+        float ss2 = 0.f, dummy2 = 0.f;
 #pragma unroll
-        for (int mi = 0; mi < MR; ++mi) {
-            const float mean = s2[mi] * inv_h;
-            ss2[mi] = 0.f;
-            if (mi < M) {
-#pragma unroll
-                for (int j = 0; j < NV; ++j)
-                    if (ok[j]) ss2[mi] += dev4(v[mi][j], mean);
-            }
-        }
+        for (int j = 0; j < NVT; ++j)
+            if (row_ok && gt + TPR * j < hv) ss2 += dev4(v[j], mean2);
         reduce(ss2, dummy2, 3);
-        if (prof_layer >= 0) stamp(prof_layer, 15);
+        if (a.prof_layer >= 0) stamp(a.prof_layer, 15);
+        const float rstd2 = rsqrtf(ss2 * inv_h + a.eps_pre * c2 * c2);
 #pragma unroll
-        for (int mi = 0; mi < MR; ++mi) {
-            if (mi < M) {
-                const float mean = s2[mi] * inv_h;
-                const float rstd = rsqrtf(ss2[mi] * inv_h + eps_pre * c2 * c2);
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    if (ok[j]) {
-                        const float4 a = v[mi][j];
-                        const uint32_t lo = pack_bf16x2((a.x - mean) * rstd * bflo(gq[j].x) + bflo(bq[j].x),
-                                                        (a.y - mean) * rstd * bfhi(gq[j].x) + bfhi(bq[j].x));
-                        const uint32_t hi = pack_bf16x2((a.z - mean) * rstd * bflo(gq[j].y) + bflo(bq[j].y),
-                                                        (a.w - mean) * rstd * bfhi(gq[j].y) + bfhi(bq[j].y));
-                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xop + mi * p.xpitch + (tid + CT * j) * 8),
-                                     "r"(lo), "r"(hi) : "memory");
-                    }
-                }
+        for (int j = 0; j < NVT; ++j) {
+            const int vi = gt + TPR * j;
+            if (row_ok && vi < hv) {
+                const uint2 gq = __ldg(reinterpret_cast<const uint2*>(a.g_pre) + vi);
+                const uint2 bq = __ldg(reinterpret_cast<const uint2*>(a.b_pre) + vi);
+                const float4 x = v[j];
+                const uint32_t lo = pack_bf16x2((x.x - mean2) * rstd2 * bflo(gq.x) + bflo(bq.x),
+                                                (x.y - mean2) * rstd2 * bfhi(gq.x) + bfhi(bq.x));
+                const uint32_t hi = pack_bf16x2((x.z - mean2) * rstd2 * bflo(gq.y) + bflo(bq.y),
+                                                (x.w - mean2) * rstd2 * bfhi(gq.y) + bfhi(bq.y));
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xop + grow * p.xpitch + vi * 8), "r"(lo), "r"(hi)
+                             : "memory");
             }
         }
         named_bar_sync(1, CT);
@@ -628,81 +597,103 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
         }
     };
 
-    // ------------------------------------------------------------------------------------------------
-    // the step
-    // ------------------------------------------------------------------------------------------------
-    const bf16* prev_post_g = nullptr;
-    const bf16* prev_post_b = nullptr;
-    for (int l = 0; l < p.L; ++l) {
-        const cv_decode_layer& Lw = p.layers[l];
-        stamp(l, 0);
-        // x = x_prev + LN4(mlp_out_prev)  (layer 0: the embedding);  xn = LN1(x)
-        if (l == 0)
-            glue(std::true_type{}, nullptr, nullptr, nullptr, p.eps, nullptr, p.resid_b,
-                 static_cast<const bf16*>(Lw.ln1_g), static_cast<const bf16*>(Lw.ln1_b), p.eps);
-        else {
-            prof_layer = l;
-            glue(std::false_type{}, p.mlp_out, prev_post_g, prev_post_b, p.eps, p.resid_a, p.resid_b,
-                 static_cast<const bf16*>(Lw.ln1_g), static_cast<const bf16*>(Lw.ln1_b), p.eps);
-            prof_layer = -1;
-        }
-        stamp(l, 1);
-        consume(make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0), EPI_BF16, static_cast<const bf16*>(Lw.b_qkv), p.qkv, 3 * h);
-        stamp(l, 2);
-        grid_barrier(100 + l);
-        stamp(l, 3);
-        attention(l);
-        stamp(l, 4);
-        grid_barrier(200 + l);
-        stamp(l, 5);
-        load_x(p.ctx, h, 0);
-        consume(make_mat(Lw.w_dense, h, h, cta, G, 0), EPI_BF16, static_cast<const bf16*>(Lw.b_dense), p.attn_out, h);
-        stamp(l, 6);
-        grid_barrier(300 + l);
-        stamp(l, 7);
-        // y = x + LN3(attn_out);  xn2 = LN2(y)
-        glue(std::false_type{}, p.attn_out, static_cast<const bf16*>(Lw.ln3_g), static_cast<const bf16*>(Lw.ln3_b), p.eps, p.resid_b,
-             p.resid_a, static_cast<const bf16*>(Lw.ln2_g), static_cast<const bf16*>(Lw.ln2_b), p.eps);
-        stamp(l, 8);
-        consume(make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0), EPI_BF16_GELU, static_cast<const bf16*>(Lw.b_fc1), p.h4, 4 * h);
-        stamp(l, 9);
-        grid_barrier(400 + l);
-        stamp(l, 10);
-        {
-            const int rg = cta / KG, kg = cta % KG;
-            load_x(p.h4, 4 * h, kg * h);
-            const Mat m2 = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, rg, G / KG, kg * h);
-            consume(m2, EPI_F32, nullptr, p.fc2_part + (size_t)kg * MAXM * h, h);
-            if (m2.r1 > m2.r0) {
-                __threadfence();
-                named_bar_sync(1, CT);
-                if (tid == 0) flags[0] = (atomicAdd(p.fc2_cnt + rg, 1u) == (unsigned int)(KG - 1)) ? 1 : 0;
-                named_bar_sync(1, CT);
-                if (flags[0]) {                          // last K quarter of this row range: sum in fixed order
-                    __threadfence();
-                    const int rows = m2.r1 - m2.r0;
-                    const bf16* b2 = static_cast<const bf16*>(Lw.b_fc2);
-                    for (int i = tid; i < M * rows; i += CT) {
-                        const int mi = i / rows, n = m2.r0 + (i - mi * rows);
-                        float v = 0.f;
+    // merge of the K quarters of the 4h->h product: the last CTA of a row range to arrive sums in fixed order
+    auto fc2_merge = [&](const Mat& m2, int rg, const bf16* b2) {
+        if (m2.r1 <= m2.r0) return;
+        __threadfence();
+        named_bar_sync(1, CT);
+        if (tid == 0) flags[0] = (atomicAdd(p.fc2_cnt + rg, 1u) == (unsigned int)(KG - 1)) ? 1 : 0;
+        named_bar_sync(1, CT);
+        if (flags[0]) {
+            __threadfence();
+            const int rows = m2.r1 - m2.r0;
+            for (int i = tid; i < M * rows; i += CT) {
+                const int mi = i / rows, n = m2.r0 + (i - mi * rows);
+                float v = 0.f;
 #pragma unroll
-                        for (int k2 = 0; k2 < KG; ++k2) v += __ldcg(p.fc2_part + ((size_t)k2 * MAXM + mi) * h + n);
-                        if (b2 != nullptr) v += __bfloat162float(b2[n]);
-                        p.mlp_out[(size_t)mi * h + n] = __float2bfloat16_rn(v);
-                    }
-                    if (tid == 0) p.fc2_cnt[rg] = 0u;
-                }
+                for (int k2 = 0; k2 < KG; ++k2) v += __ldcg(p.fc2_part + ((size_t)k2 * MAXM + mi) * h + n);
+                if (b2 != nullptr) v += __bfloat162float(b2[n]);
+                p.mlp_out[(size_t)mi * h + n] = __float2bfloat16_rn(v);
             }
+            if (tid == 0) p.fc2_cnt[rg] = 0u;
         }
-        stamp(l, 11);
-        grid_barrier(500 + l);
-        stamp(l, 12);
-        prev_post_g = static_cast<const bf16*>(Lw.ln4_g);
-        prev_post_b = static_cast<const bf16*>(Lw.ln4_b);
+    };
+
+    // ------------------------------------------------------------------------------------------------
+    // the step: 5 phases per layer (each ends in a grid barrier), then final LayerNorm + logits
+    //   0: x = x_prev + LN4(mlp_out_prev) (layer 0: embedding), LN1, QKV      1: attention over the K|V cache
+    //   2: dense                3: y = x + LN3(attn_out), LN2, h->4h + GELU    4: 4h->h (K quarters) + merge
+    // ------------------------------------------------------------------------------------------------
+    const int n_it = 5 * p.L + 1;
+    const int rg = cta / KG, kg = cta % KG;
+    for (int it = 0; it < n_it; ++it) {
+        const int l = it / 5, phs = it - 5 * l;
+        const bool fin = it == n_it - 1;
+        const cv_decode_layer& Lw = p.layers[fin ? p.L - 1 : l];
+        if (!fin && phs == 0) stamp(l, 0);
+        // ---- glue ----
+        if (fin || phs == 0 || phs == 3) {
+            GlueArgs ga;
+            ga.eps_post = p.eps;
+            ga.eps_pre = p.eps;
+            ga.prof_layer = -1;
+            if (fin) {
+                ga.gemm_out = p.mlp_out; ga.g_post = static_cast<const bf16*>(Lw.ln4_g); ga.b_post = static_cast<const bf16*>(Lw.ln4_b);
+                ga.res_in = p.resid_a; ga.res_out = nullptr;
+                ga.g_pre = p.lnf_g; ga.b_pre = p.lnf_b; ga.eps_pre = p.eps_final;
+            } else if (phs == 0) {
+                const cv_decode_layer& Lp = p.layers[l > 0 ? l - 1 : 0];
+                ga.gemm_out = l > 0 ? p.mlp_out : nullptr;
+                ga.g_post = static_cast<const bf16*>(Lp.ln4_g); ga.b_post = static_cast<const bf16*>(Lp.ln4_b);
+                ga.res_in = p.resid_a; ga.res_out = p.resid_b;
+                ga.g_pre = static_cast<const bf16*>(Lw.ln1_g); ga.b_pre = static_cast<const bf16*>(Lw.ln1_b);
+                ga.prof_layer = l > 0 ? l : -1;
+            } else {
+                ga.gemm_out = p.attn_out; ga.g_post = static_cast<const bf16*>(Lw.ln3_g); ga.b_post = static_cast<const bf16*>(Lw.ln3_b);
+                ga.res_in = p.resid_b; ga.res_out = p.resid_a;
+                ga.g_pre = static_cast<const bf16*>(Lw.ln2_g); ga.b_pre = static_cast<const bf16*>(Lw.ln2_b);
+            }
+            if (it == 0) glue(std::true_type{}, ga);
+            else glue(std::false_type{}, ga);
+            if (!fin) stamp(l, phs == 0 ? 1 : 8);
+        }
+        // ---- activation operand written by other CTAs ----
+        if (!fin && (phs == 2 || phs == 4)) {
+            if (phs == 2) load_x(p.ctx, h, 0);
+            else load_x(p.h4, 4 * h, kg * h);
+        }
+        // ---- the phase's work ----
+        if (!fin && phs == 1) {
+            attention(l);
+        } else {
+            Mat m;
+            int epi = EPI_BF16;
+            const bf16* bias = nullptr;
+            void* out = nullptr;
+            int64_t ldo = h;
+            if (fin) {
+                m = make_mat(p.wte, h, p.V, cta, G, 0); epi = EPI_F32; out = p.logits; ldo = p.ldl;
+            } else if (phs == 0) {
+                m = make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0); bias = static_cast<const bf16*>(Lw.b_qkv); out = p.qkv; ldo = 3 * h;
+            } else if (phs == 2) {
+                m = make_mat(Lw.w_dense, h, h, cta, G, 0); bias = static_cast<const bf16*>(Lw.b_dense); out = p.attn_out;
+            } else if (phs == 3) {
+                m = make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0); epi = EPI_BF16_GELU; bias = static_cast<const bf16*>(Lw.b_fc1);
+                out = p.h4; ldo = 4 * h;
+            } else {
+                m = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, rg, G / KG, kg * h); epi = EPI_F32;
+                out = p.fc2_part + (size_t)kg * MAXM * h;
+            }
+            consume(m, epi, bias, out, ldo);
+            if (!fin && phs == 4) fc2_merge(m, rg, static_cast<const bf16*>(Lw.b_fc2));
+        }
+        if (!fin) {
+            const int after_work = phs == 0 ? 2 : (phs == 1 ? 4 : (phs == 2 ? 6 : (phs == 3 ? 9 : 11)));
+            stamp(l, after_work);
+            grid_barrier(100 * (phs + 1) + l);
+            stamp(l, after_work + 1);
+        }
     }
-    // final: x = x + LN4(mlp_out);  logits = LN_f(x) wte^T
-    glue(std::false_type{}, p.mlp_out, prev_post_g, prev_post_b, p.eps, p.resid_a, nullptr, p.lnf_g, p.lnf_b, p.eps_final);
-    consume(make_mat(p.wte, h, p.V, cta, G, 0), EPI_F32, nullptr, p.logits, p.ldl);
     if (cta == 0 && tid == 0) *p.bar_base = bar_target;
 }
 
