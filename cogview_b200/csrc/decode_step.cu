@@ -50,7 +50,8 @@ constexpr int KG = 4;               // K groups of the 4h->h matrix
 constexpr int HD = 64;              // head dim
 constexpr int MAXST = 8;            // ring stages (upper bound)
 constexpr int MAXM = 8;
-constexpr int AUNR = 4;             // attention: 4-key groups in flight per warp iteration (16 keys)
+constexpr int KVB = 64;             // keys per K|V ring stage (16 warps x 4 keys)
+constexpr int KVB_MAX = 64;         // key blocks per (sequence, head): max_len <= KVB * KVB_MAX = 4096
 constexpr int PART_STRIDE = HD + 2; // attention partial: acc[64], m, l
 
 struct Params {
@@ -66,8 +67,9 @@ struct Params {
     int64_t ldl;
     // workspace
     bf16 *qkv, *ctx, *attn_out, *h4, *mlp_out;
-    float *resid_a, *resid_b, *fc2_part, *attn_part;
-    unsigned int *attn_cnt, *fc2_cnt;
+    float *resid_a, *resid_b, *attn_part;
+    long long* fc2_acc;            // [2][MAXM][h] fixed-point (2^-40) sums of the 4h->h K quarters, see EPI_FIX64
+    unsigned int* attn_cnt;
     unsigned long long *bar_ctr, *bar_base;
     int* err;
     unsigned long long* prof;      // optional [grid][L][16] globaltimer stamps of the phase boundaries
@@ -98,6 +100,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_u32(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ uint64_t evict_first_policy() {
@@ -143,10 +152,16 @@ __device__ __forceinline__ Mat make_mat(const void* W, int64_t ldw, int N, int p
     return m;
 }
 
-enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_F32 = 2 };
+// EPI_FIX64: the four K quarters of the 4h->h product are summed by red.global.add.u64 on 2^-40 fixed-point images of
+// the fp32 partial sums: integer addition is associative, so the result does not depend on the arrival order (a float
+// atomic would make the step non-reproducible) and no merge pass / arrival counter is needed.
+enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_F32 = 2, EPI_FIX64 = 3 };
+constexpr float FIX_SCALE = 1099511627776.0f;          // 2^40
+constexpr float FIX_INV = 1.0f / 1099511627776.0f;
 
 template <int MR, int CPW>
-__global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constant__ Params p,
+                                                            const __grid_constant__ CUtensorMap tmKV) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, G = gridDim.x;
@@ -164,7 +179,7 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
         flags[1] = p.quiet;
         for (int i = 0; i < p.nst; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], GW);
+            mbar_init(&empty[i], CW);
         }
         fence_barrier_init();
     }
@@ -208,6 +223,25 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 else m = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, cta / KG, G / KG, (cta % KG) * h);
             }
             produce(m);
+            if (it < 4 * p.L && which == 0) {             // this CTA's K|V key blocks of layer l follow its QKV weights
+                const int t = __ldg(p.cur_len);
+                const int nblk = (t + KVB - 1) / KVB;
+                const long long NBt = (long long)p.M * p.heads * nblk;
+                const int f0 = (int)((NBt * cta) / G), f1 = (int)((NBt * (cta + 1)) / G);
+                for (int f = f0; f < f1; ++f) {
+                    const int bh = f / nblk, blk = f - bh * nblk;
+                    const int head = bh % p.heads, batch = bh / p.heads;
+                    mbar_wait(&empty[st], ph ^ 1);
+                    if (lane == 0) {
+                        mbar_expect_tx(&full[st], 2 * KVB * 128);
+                        const uint32_t dst = ring + st * p.stage_bytes;
+                        tma_load_4d_u32(dst, &tmKV, smem_u32(&full[st]), head * HD, blk * KVB, batch, l);
+                        tma_load_4d_u32(dst + KVB * 128, &tmKV, smem_u32(&full[st]), h + head * HD, blk * KVB, batch, l);
+                    }
+                    __syncwarp();
+                    if (++st == p.nst) { st = 0; ph ^= 1; }
+                }
+            }
         }
         return;
     }
@@ -284,6 +318,8 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[st]);
+                } else if (lane == 0) {
+                    mbar_arrive(&empty[st]);                // not this group's stage: nothing to read
                 }
                 ++sq;
                 if (++st == p.nst) { st = 0; ph ^= 1; }
@@ -304,6 +340,9 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 if (mi < M && n < m.r1) {
                     if (epi == EPI_F32) {
                         static_cast<float*>(out)[(size_t)mi * ldo + n] = v;
+                    } else if (epi == EPI_FIX64) {
+                        atomicAdd(static_cast<unsigned long long*>(out) + (size_t)mi * ldo + n,
+                                  (unsigned long long)__float2ll_rn(v * FIX_SCALE));
                     } else {
                         if (bias != nullptr) v += __bfloat162float(bias[n]);
                         if (epi == EPI_BF16_GELU) v = gelu_tanh(v);
@@ -337,6 +376,8 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
     constexpr int NVT = (2560 / 4 + TPR - 1) / TPR;
     struct GlueArgs {
         const bf16 *gemm_out, *g_post, *b_post;
+        const long long* acc;          // != nullptr: gemm_out = bf16(acc * 2^-40 + acc_bias) (the 4h->h output)
+        const bf16* acc_bias;
         const float* res_in;
         float* res_out;
         const bf16 *g_pre, *b_pre;
@@ -372,36 +413,75 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint2* wrow = nullptr;
         const uint2* prow = nullptr;
-        if (EMB && row_ok) {
-            wrow = reinterpret_cast<const uint2*>(p.wte + (size_t)__ldg(p.ids + grow) * h);
-            prow = reinterpret_cast<const uint2*>(p.wpe + (size_t)__ldg(p.pos + grow) * h);
+        if (EMB) {                                   // rows >= M read row 0 (discarded)
+            const int rr = row_ok ? grow : 0;
+            wrow = reinterpret_cast<const uint2*>(p.wte + (size_t)__ldg(p.ids + rr) * h);
+            prow = reinterpret_cast<const uint2*>(p.wpe + (size_t)__ldg(p.pos + rr) * h);
         }
-        auto residual = [&](int vi) -> float4 {
-            if (!EMB) return __ldcg(reinterpret_cast<const float4*>(a.res_in) + grow * hv + vi);
+        auto residual = [&](int row, int vi) -> float4 {
+            if (!EMB) return __ldcg(reinterpret_cast<const float4*>(a.res_in) + row * hv + vi);
             const uint2 x = __ldg(wrow + vi), y = __ldg(prow + vi);
             return make_float4(bflo(x.x) + bflo(y.x), bfhi(x.x) + bfhi(y.x), bflo(x.y) + bflo(y.y), bfhi(x.y) + bfhi(y.y));
         };
 
-        float4 v[NVT];
-        if (a.gemm_out != nullptr) {
-            float s = 0.f, amax = 0.f;
+        // Every global load below is UNCONDITIONAL (clamped index, value discarded by a select): loads inside
+        // `if (in range)` branches are not hoisted by the compiler, and the first version of this routine paid one
+        // serialised L2 round trip per vector (5 x ~0.7 us per pass).
+        int vc[NVT];
+        bool ok[NVT];
+#pragma unroll
+        for (int j = 0; j < NVT; ++j) {
+            const int vi = gt + TPR * j;
+            ok[j] = row_ok && vi < hv;
+            vc[j] = ok[j] ? vi : 0;
+        }
+        const int growc = row_ok ? grow : 0;
+        const bool has_post = !EMB && (a.gemm_out != nullptr || a.acc != nullptr);   // layer 0 starts from the embedding
+        constexpr bool PRE = MR <= 4;               // small batches: parameters and residual are fetched up front
+        uint2 gq[PRE ? NVT : 1], bq[PRE ? NVT : 1];
+        if (PRE) {
 #pragma unroll
             for (int j = 0; j < NVT; ++j) {
-                const int vi = gt + TPR * j;
-                uint2 u = make_uint2(0u, 0u);
-                if (row_ok && vi < hv) u = __ldcg(reinterpret_cast<const uint2*>(a.gemm_out) + grow * hv + vi);
-                v[j] = make_float4(bflo(u.x), bfhi(u.x), bflo(u.y), bfhi(u.y));
-                s += sum4(v[j]);
-                amax = fmaxf(amax, amax4(v[j]));
+                gq[PRE ? j : 0] = __ldg(reinterpret_cast<const uint2*>(a.g_pre) + vc[j]);
+                bq[PRE ? j : 0] = __ldg(reinterpret_cast<const uint2*>(a.b_pre) + vc[j]);
             }
-            constexpr bool PRE = MR <= 4;               // small batches: the residual is fetched under the first reduction
-            float4 rs[PRE ? NVT : 1];
-            if (PRE) {
+        }
+        float4 v[NVT];
+        if (has_post) {
+            uint2 gp[NVT], bp[NVT];
+#pragma unroll
+            for (int j = 0; j < NVT; ++j) {
+                gp[j] = __ldg(reinterpret_cast<const uint2*>(a.g_post) + vc[j]);
+                bp[j] = __ldg(reinterpret_cast<const uint2*>(a.b_post) + vc[j]);
+            }
+            float s = 0.f, amax = 0.f;
+            if (a.acc != nullptr) {
 #pragma unroll
                 for (int j = 0; j < NVT; ++j) {
-                    const int vi = gt + TPR * j;
-                    rs[PRE ? j : 0] = (row_ok && vi < hv) ? residual(vi) : zero4;
+                    const longlong2* src = reinterpret_cast<const longlong2*>(a.acc) + (growc * hv + vc[j]) * 2;
+                    const longlong2 a01 = __ldcg(src), a23 = __ldcg(src + 1);
+                    const uint2 bb = __ldg(reinterpret_cast<const uint2*>(a.acc_bias) + vc[j]);
+                    // the 4h->h output as the per-operation path produces it: bf16(sum + bias)
+                    const uint32_t lo = pack_bf16x2(__ll2float_rn(a01.x) * FIX_INV + bflo(bb.x),
+                                                    __ll2float_rn(a01.y) * FIX_INV + bfhi(bb.x));
+                    const uint32_t hi = pack_bf16x2(__ll2float_rn(a23.x) * FIX_INV + bflo(bb.y),
+                                                    __ll2float_rn(a23.y) * FIX_INV + bfhi(bb.y));
+                    v[j] = ok[j] ? make_float4(bflo(lo), bfhi(lo), bflo(hi), bfhi(hi)) : zero4;
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NVT; ++j) {
+                    const uint2 u = __ldcg(reinterpret_cast<const uint2*>(a.gemm_out) + growc * hv + vc[j]);
+                    v[j] = ok[j] ? make_float4(bflo(u.x), bfhi(u.x), bflo(u.y), bfhi(u.y)) : zero4;
+                }
+            }
+            float4 rs[NVT];
+#pragma unroll
+            for (int j = 0; j < NVT; ++j) rs[j] = residual(growc, vc[j]);
+#pragma unroll
+            for (int j = 0; j < NVT; ++j) {
+                s += sum4(v[j]);
+                amax = fmaxf(amax, amax4(v[j]));
             }
             reduce(s, amax, 0);
             if (a.prof_layer >= 0) stamp(a.prof_layer, 13);
@@ -409,30 +489,23 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
             float ss = 0.f, dummy = 0.f;
 #pragma unroll
             for (int j = 0; j < NVT; ++j)
-                if (gt + TPR * j < hv) ss += dev4(v[j], mean);
+                if (ok[j]) ss += dev4(v[j], mean);
             reduce(ss, dummy, 1);
             const float rstd = rsqrtf(ss * inv_h + a.eps_post * c * c);
 #pragma unroll
             for (int j = 0; j < NVT; ++j) {
-                const int vi = gt + TPR * j;
-                if (row_ok && vi < hv) {
-                    const uint2 gp = __ldg(reinterpret_cast<const uint2*>(a.g_post) + vi);
-                    const uint2 bp = __ldg(reinterpret_cast<const uint2*>(a.b_post) + vi);
-                    const float4 r = PRE ? rs[PRE ? j : 0] : residual(vi);
-                    float4& x = v[j];
-                    x.x = (x.x - mean) * rstd * bflo(gp.x) + bflo(bp.x) + r.x;
-                    x.y = (x.y - mean) * rstd * bfhi(gp.x) + bfhi(bp.x) + r.y;
-                    x.z = (x.z - mean) * rstd * bflo(gp.y) + bflo(bp.y) + r.z;
-                    x.w = (x.w - mean) * rstd * bfhi(gp.y) + bfhi(bp.y) + r.w;
-                } else {
-                    v[j] = zero4;
-                }
+                float4 x = v[j];
+                x.x = (x.x - mean) * rstd * bflo(gp[j].x) + bflo(bp[j].x) + rs[j].x;
+                x.y = (x.y - mean) * rstd * bfhi(gp[j].x) + bfhi(bp[j].x) + rs[j].y;
+                x.z = (x.z - mean) * rstd * bflo(gp[j].y) + bflo(bp[j].y) + rs[j].z;
+                x.w = (x.w - mean) * rstd * bfhi(gp[j].y) + bfhi(bp[j].y) + rs[j].w;
+                v[j] = ok[j] ? x : zero4;
             }
         } else {
 #pragma unroll
             for (int j = 0; j < NVT; ++j) {
-                const int vi = gt + TPR * j;
-                v[j] = (row_ok && vi < hv) ? residual(vi) : zero4;
+                const float4 r = residual(growc, vc[j]);
+                v[j] = ok[j] ? r : zero4;
             }
         }
         // residual stream out (owner slice), statistics of v
@@ -441,11 +514,17 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < NVT; ++j) {
             const int vi = gt + TPR * j;
-            if (row_ok && vi < hv) {
-                if (a.res_out != nullptr && vi >= v_lo && vi < v_hi)
-                    *(reinterpret_cast<float4*>(a.res_out) + grow * hv + vi) = v[j];
-                s2 += sum4(v[j]);
-                amax2 = fmaxf(amax2, amax4(v[j]));
+            if (ok[j] && a.res_out != nullptr && vi >= v_lo && vi < v_hi)
+                *(reinterpret_cast<float4*>(a.res_out) + grow * hv + vi) = v[j];
+            s2 += sum4(v[j]);
+            amax2 = fmaxf(amax2, amax4(v[j]));
+        }
+        uint2 gq2[PRE ? 1 : NVT], bq2[PRE ? 1 : NVT];
+        if (!PRE) {
+#pragma unroll
+            for (int j = 0; j < NVT; ++j) {
+                gq2[PRE ? 0 : j] = __ldg(reinterpret_cast<const uint2*>(a.g_pre) + vc[j]);
+                bq2[PRE ? 0 : j] = __ldg(reinterpret_cast<const uint2*>(a.b_pre) + vc[j]);
             }
         }
         reduce(s2, amax2, 2);
@@ -454,98 +533,108 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
         float ss2 = 0.f, dummy2 = 0.f;
 #pragma unroll
         for (int j = 0; j < NVT; ++j)
-            if (row_ok && gt + TPR * j < hv) ss2 += dev4(v[j], mean2);
+            if (ok[j]) ss2 += dev4(v[j], mean2);
         reduce(ss2, dummy2, 3);
         if (a.prof_layer >= 0) stamp(a.prof_layer, 15);
         const float rstd2 = rsqrtf(ss2 * inv_h + a.eps_pre * c2 * c2);
 #pragma unroll
         for (int j = 0; j < NVT; ++j) {
-            const int vi = gt + TPR * j;
-            if (row_ok && vi < hv) {
-                const uint2 gq = __ldg(reinterpret_cast<const uint2*>(a.g_pre) + vi);
-                const uint2 bq = __ldg(reinterpret_cast<const uint2*>(a.b_pre) + vi);
-                const float4 x = v[j];
-                const uint32_t lo = pack_bf16x2((x.x - mean2) * rstd2 * bflo(gq.x) + bflo(bq.x),
-                                                (x.y - mean2) * rstd2 * bfhi(gq.x) + bfhi(bq.x));
-                const uint32_t hi = pack_bf16x2((x.z - mean2) * rstd2 * bflo(gq.y) + bflo(bq.y),
-                                                (x.w - mean2) * rstd2 * bfhi(gq.y) + bfhi(bq.y));
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xop + grow * p.xpitch + vi * 8), "r"(lo), "r"(hi)
-                             : "memory");
-            }
+            const uint2 gg = PRE ? gq[PRE ? j : 0] : gq2[PRE ? 0 : j];
+            const uint2 bb = PRE ? bq[PRE ? j : 0] : bq2[PRE ? 0 : j];
+            const float4 x = v[j];
+            const uint32_t lo = pack_bf16x2((x.x - mean2) * rstd2 * bflo(gg.x) + bflo(bb.x),
+                                            (x.y - mean2) * rstd2 * bfhi(gg.x) + bfhi(bb.x));
+            const uint32_t hi = pack_bf16x2((x.z - mean2) * rstd2 * bflo(gg.y) + bflo(bb.y),
+                                            (x.w - mean2) * rstd2 * bfhi(gg.y) + bfhi(bb.y));
+            if (ok[j])
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xop + grow * p.xpitch + (gt + TPR * j) * 8), "r"(lo),
+                             "r"(hi) : "memory");
         }
         named_bar_sync(1, CT);
     };
 
-    // attention of the new token over keys 0..t (standard_attention for sq = 1), K|V cache of layer l
+    // attention of the new token over keys 0..t (standard_attention for sq = 1).  The cached keys reach the CTA through
+    // the same ring as the weights: the producer streams [64 keys x 64 dims] K and V tiles of this CTA's share of the
+    // flattened (sequence, head, key block) space right after the QKV weights — cached keys do not depend on this
+    // step, so they are on their way while QKV is still being multiplied and no DRAM latency is exposed here.
+    // A stage is worked on by all 16 warps (4 keys per warp, 8 lanes per key); a warp keeps its online-softmax
+    // state across the consecutive blocks of a (sequence, head) pair; at the end of a pair the 16 warp states are
+    // merged through shared memory, and pairs that straddle CTAs through L2 partials + an arrival counter
+    // (fixed merge order: deterministic).  The new token's K/V come from the QKV output and are appended in place.
     auto attention = [&](int l) {
         bf16* cache_l = p.cache + (size_t)l * p.cache_ls;
         const int grp = lane >> 3, sub = lane & 7;
-        const int t = t_cached, T = t + 1, S = p.S;
-        const int per = (T + S - 1) / S;
-        const int U = M * p.heads * S;
-        for (int u = cta + G * warp; u < U; u += G * CW) {
-            const int s = u % S, bh = u / S;
+        const int t = t_cached;
+        const int nblk = (t + KVB - 1) / KVB;
+        const int pairs = M * p.heads;
+        const long long NBt = (long long)pairs * nblk;
+        const int f0 = (int)((NBt * cta) / G), f1 = (int)((NBt * (cta + 1)) / G);
+        float* sm_acc = part;                                 // [CW][HD] warp states (aliases the tile partials)
+        float* sm_ml = red;                                   // [CW][2]
+        auto lo_of = [&](int c) { return (int)((NBt * c) / G); };
+        auto owner = [&](int f) {
+            int c = (int)(((long long)f * G) / NBt);
+            while (lo_of(c + 1) <= f) ++c;
+            return c;
+        };
+        float qf[8], m = -INFINITY, lsum = 0.f, acc[8];
+        int cur = -1;
+        auto start_pair = [&](int bh) {
             const int head = bh % p.heads, batch = bh / p.heads;
-            const bf16* qrow = p.qkv + (size_t)batch * 3 * h + head * HD + sub * 8;
-            float qf[8];
-            bf16x8_to_float(ldcg_u128(qrow), qf);
-            const uint4 knew = ldcg_u128(qrow + h);
-            const uint4 vnew = ldcg_u128(qrow + 2 * h);
-            bf16* kbase = cache_l + (size_t)batch * p.cache_bs + head * HD + sub * 8;
-            if (s == S - 1 && grp == 0 && t < p.max_len) {
-                *reinterpret_cast<uint4*>(kbase + (size_t)t * 2 * h) = knew;
-                *reinterpret_cast<uint4*>(kbase + (size_t)t * 2 * h + h) = vnew;
-            }
-            const int j0 = s * per, j1 = min(T, j0 + per);
-            float m = -INFINITY, lsum = 0.f, acc[8];
+            bf16x8_to_float(ldcg_u128(p.qkv + (size_t)batch * 3 * h + head * HD + sub * 8), qf);
+            m = -INFINITY;
+            lsum = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-            for (int jb = j0; jb < j1; jb += 4 * AUNR) {
-                uint4 kr[AUNR], vr[AUNR];
-                bool valid[AUNR];
+        };
+        auto add_key = [&](const uint4& kr, const uint4& vr, bool valid) {
+            float kf[8];
+            bf16x8_to_float(kr, kf);
+            float sdot = 0.f;
 #pragma unroll
-                for (int a = 0; a < AUNR; ++a) {
-                    const int j = jb + a * 4 + grp;
-                    valid[a] = j < j1;
-                    kr[a] = knew;
-                    vr[a] = vnew;
-                    if (valid[a] && j != t) {
-                        const bf16* kp = kbase + (size_t)j * 2 * h;
-                        kr[a] = __ldg(reinterpret_cast<const uint4*>(kp));
-                        vr[a] = __ldg(reinterpret_cast<const uint4*>(kp + h));
+            for (int i = 0; i < 8; ++i) sdot = fmaf(qf[i], kf[i], sdot);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+            if (valid) {
+                const float sc = sdot * p.scale_log2;
+                const float mn = fmaxf(m, sc);
+                const float alpha = exp2f(m - mn), pr = exp2f(sc - mn);
+                float vf[8];
+                bf16x8_to_float(vr, vf);
+                m = mn;
+                lsum = lsum * alpha + pr;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i] * alpha);
+            }
+        };
+        auto finish_pair = [&](int bh) {
+            const int head = bh % p.heads, batch = bh / p.heads;
+            // contributors of this pair = distinct owners of its key blocks (non-decreasing in the block index)
+            int ncontrib = 1, my_idx = 0;
+            bool owns_last = true;
+            if (nblk > 0) {
+                int prev = -1;
+                ncontrib = 0;
+                for (int bq = 0; bq < nblk; ++bq) {
+                    const int o = owner(bh * nblk + bq);
+                    if (o != prev) {
+                        if (o == cta) my_idx = ncontrib;
+                        ++ncontrib;
+                        prev = o;
                     }
                 }
-                float sc[AUNR];
-                float mn = m;
-#pragma unroll
-                for (int a = 0; a < AUNR; ++a) {
-                    float kf[8];
-                    bf16x8_to_float(kr[a], kf);
-                    float sdot = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) sdot = fmaf(qf[i], kf[i], sdot);
-                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-                    sc[a] = valid[a] ? sdot * p.scale_log2 : -INFINITY;
-                    mn = fmaxf(mn, sc[a]);
+                owns_last = prev == cta;
+            }
+            if (owns_last && warp == 0) {                     // the new token: key index t, K/V from the QKV output
+                const bf16* qrow = p.qkv + (size_t)batch * 3 * h + head * HD + sub * 8;
+                const uint4 knew = ldcg_u128(qrow + h), vnew = ldcg_u128(qrow + 2 * h);
+                if (grp == 0 && t < p.max_len) {
+                    bf16* kdst = cache_l + (size_t)batch * p.cache_bs + (size_t)t * 2 * h + head * HD + sub * 8;
+                    *reinterpret_cast<uint4*>(kdst) = knew;
+                    *reinterpret_cast<uint4*>(kdst + h) = vnew;
                 }
-                if (mn > -INFINITY) {
-                    const float alpha = exp2f(m - mn);
-                    m = mn;
-                    lsum *= alpha;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] *= alpha;
-#pragma unroll
-                    for (int a = 0; a < AUNR; ++a) {
-                        const float pr = exp2f(sc[a] - mn);
-                        float vf[8];
-                        bf16x8_to_float(vr[a], vf);
-                        lsum += pr;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
-                    }
-                }
+                add_key(knew, vnew, grp == 0);
             }
             // merge the warp's four key groups (lanes with the same `sub`)
 #pragma unroll
@@ -563,59 +652,88 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 }
                 m = mn;
             }
-            float* dst = p.attn_part + (size_t)u * PART_STRIDE;
             if (grp == 0) {
-                *reinterpret_cast<float2*>(dst + sub * 8) = make_float2(acc[0], acc[1]);
-                *reinterpret_cast<float2*>(dst + sub * 8 + 2) = make_float2(acc[2], acc[3]);
-                *reinterpret_cast<float2*>(dst + sub * 8 + 4) = make_float2(acc[4], acc[5]);
-                *reinterpret_cast<float2*>(dst + sub * 8 + 6) = make_float2(acc[6], acc[7]);
-                if (sub == 0) *reinterpret_cast<float2*>(dst + HD) = make_float2(m, lsum);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sm_acc[warp * HD + sub * 8 + i] = acc[i];
+                if (sub == 0) { sm_ml[2 * warp] = m; sm_ml[2 * warp + 1] = lsum; }
             }
-            __threadfence();
-            __syncwarp();
-            unsigned int old = 0;
-            if (lane == 0) old = atomicAdd(p.attn_cnt + bh, 1u);
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (old == (unsigned int)(S - 1)) {            // last unit of this (sequence, head): merge in split order
-                __threadfence();
-                const float* src = p.attn_part + (size_t)bh * S * PART_STRIDE;
+            named_bar_sync(1, CT);
+            if (tid < HD) {
                 float Mx = -INFINITY;
-                for (int s2 = 0; s2 < S; ++s2) Mx = fmaxf(Mx, __ldcg(src + s2 * PART_STRIDE + HD));
-                float Ls = 0.f, A0 = 0.f, A1 = 0.f;
-                for (int s2 = 0; s2 < S; ++s2) {
-                    const float ms = __ldcg(src + s2 * PART_STRIDE + HD);
-                    const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - Mx);
-                    Ls += __ldcg(src + s2 * PART_STRIDE + HD + 1) * w;
-                    A0 += __ldcg(src + s2 * PART_STRIDE + lane) * w;
-                    A1 += __ldcg(src + s2 * PART_STRIDE + 32 + lane) * w;
+#pragma unroll
+                for (int w = 0; w < CW; ++w) Mx = fmaxf(Mx, sm_ml[2 * w]);
+                float Ls = 0.f, A = 0.f;
+#pragma unroll
+                for (int w = 0; w < CW; ++w) {
+                    const float mw = sm_ml[2 * w];
+                    const float wgt = (mw == -INFINITY) ? 0.f : exp2f(mw - Mx);
+                    Ls += sm_ml[2 * w + 1] * wgt;
+                    A += sm_acc[w * HD + tid] * wgt;
                 }
                 bf16* o = p.ctx + (size_t)batch * h + head * HD;
-                o[lane] = __float2bfloat16_rn(A0 / Ls);
-                o[lane + 32] = __float2bfloat16_rn(A1 / Ls);
-                if (lane == 0) p.attn_cnt[bh] = 0u;
+                if (ncontrib == 1) {
+                    o[tid] = __float2bfloat16_rn(A / Ls);
+                } else {
+                    float* dst = p.attn_part + ((size_t)bh * KVB_MAX + my_idx) * PART_STRIDE;
+                    dst[tid] = A;
+                    if (tid == 0) { dst[HD] = Mx; dst[HD + 1] = Ls; }
+                    __threadfence();
+                    named_bar_sync(2, HD);
+                    if (tid == 0) flags[0] = (atomicAdd(p.attn_cnt + bh, 1u) == (unsigned int)(ncontrib - 1)) ? 1 : 0;
+                    named_bar_sync(2, HD);
+                    if (flags[0]) {                          // last contributor: merge in contributor order
+                        __threadfence();
+                        const float* src = p.attn_part + (size_t)bh * KVB_MAX * PART_STRIDE;
+                        float M2 = -INFINITY;
+                        for (int c2 = 0; c2 < ncontrib; ++c2) M2 = fmaxf(M2, __ldcg(src + c2 * PART_STRIDE + HD));
+                        float L2 = 0.f, A2 = 0.f;
+                        for (int c2 = 0; c2 < ncontrib; ++c2) {
+                            const float ms = __ldcg(src + c2 * PART_STRIDE + HD);
+                            const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - M2);
+                            L2 += __ldcg(src + c2 * PART_STRIDE + HD + 1) * wgt;
+                            A2 += __ldcg(src + c2 * PART_STRIDE + tid) * wgt;
+                        }
+                        o[tid] = __float2bfloat16_rn(A2 / L2);
+                        if (tid == 0) p.attn_cnt[bh] = 0u;
+                    }
+                }
             }
+            named_bar_sync(1, CT);                            // sm_acc / sm_ml / flags free for the next pair
+        };
+
+        if (nblk == 0) {                                      // empty cache: only the new token, pairs round-robin
+            for (int bh = cta; bh < pairs; bh += G) {
+                start_pair(bh);
+                finish_pair(bh);
+            }
+            return;
         }
+        for (int f = f0; f < f1; ++f) {
+            const int bh = f / nblk, blk = f - bh * nblk;
+            if (bh != cur) {
+                if (cur >= 0) finish_pair(cur);
+                start_pair(bh);
+                cur = bh;
+            }
+            mbar_wait(&full[st], ph);
+            const uint32_t ka = ring + st * p.stage_bytes + (warp * 4 + grp) * 128 + sub * 16;
+            const uint4 kr = lds128(ka), vr = lds128(ka + KVB * 128);
+            add_key(kr, vr, blk * KVB + warp * 4 + grp < t);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+            ++sq;
+            if (++st == p.nst) { st = 0; ph ^= 1; }
+        }
+        if (cur >= 0) finish_pair(cur);
     };
 
-    // merge of the K quarters of the 4h->h product: the last CTA of a row range to arrive sums in fixed order
-    auto fc2_merge = [&](const Mat& m2, int rg, const bf16* b2) {
-        if (m2.r1 <= m2.r0) return;
-        __threadfence();
-        named_bar_sync(1, CT);
-        if (tid == 0) flags[0] = (atomicAdd(p.fc2_cnt + rg, 1u) == (unsigned int)(KG - 1)) ? 1 : 0;
-        named_bar_sync(1, CT);
-        if (flags[0]) {
-            __threadfence();
-            const int rows = m2.r1 - m2.r0;
-            for (int i = tid; i < M * rows; i += CT) {
-                const int mi = i / rows, n = m2.r0 + (i - mi * rows);
-                float v = 0.f;
-#pragma unroll
-                for (int k2 = 0; k2 < KG; ++k2) v += __ldcg(p.fc2_part + ((size_t)k2 * MAXM + mi) * h + n);
-                if (b2 != nullptr) v += __bfloat162float(b2[n]);
-                p.mlp_out[(size_t)mi * h + n] = __float2bfloat16_rn(v);
-            }
-            if (tid == 0) p.fc2_cnt[rg] = 0u;
+    // owner slice of a fixed-point accumulator back to zero (its next use is two layers ahead)
+    auto zero_acc = [&](long long* acc) {
+        const int hv2 = h >> 1;                             // 16-byte (2 x int64) vectors per row
+        const int lo = (int)(((int64_t)hv2 * cta) / G), hi = (int)(((int64_t)hv2 * (cta + 1)) / G);
+        for (int i = tid; i < MAXM * (hi - lo); i += CT) {
+            const int mi = i / (hi - lo), c = lo + (i - mi * (hi - lo));
+            reinterpret_cast<longlong2*>(acc)[(size_t)mi * hv2 + c] = make_longlong2(0ll, 0ll);
         }
     };
 
@@ -626,6 +744,8 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
     // ------------------------------------------------------------------------------------------------
     const int n_it = 5 * p.L + 1;
     const int rg = cta / KG, kg = cta % KG;
+    zero_acc(p.fc2_acc);                                    // both accumulators: first use is 4 grid barriers away
+    zero_acc(p.fc2_acc + (size_t)MAXM * h);
     for (int it = 0; it < n_it; ++it) {
         const int l = it / 5, phs = it - 5 * l;
         const bool fin = it == n_it - 1;
@@ -637,13 +757,20 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
             ga.eps_post = p.eps;
             ga.eps_pre = p.eps;
             ga.prof_layer = -1;
+            ga.acc = nullptr;
+            ga.acc_bias = nullptr;
             if (fin) {
-                ga.gemm_out = p.mlp_out; ga.g_post = static_cast<const bf16*>(Lw.ln4_g); ga.b_post = static_cast<const bf16*>(Lw.ln4_b);
+                ga.gemm_out = nullptr; ga.acc = p.fc2_acc + (size_t)((p.L - 1) & 1) * MAXM * h;
+                ga.acc_bias = static_cast<const bf16*>(Lw.b_fc2); ga.g_post = static_cast<const bf16*>(Lw.ln4_g); ga.b_post = static_cast<const bf16*>(Lw.ln4_b);
                 ga.res_in = p.resid_a; ga.res_out = nullptr;
                 ga.g_pre = p.lnf_g; ga.b_pre = p.lnf_b; ga.eps_pre = p.eps_final;
             } else if (phs == 0) {
                 const cv_decode_layer& Lp = p.layers[l > 0 ? l - 1 : 0];
-                ga.gemm_out = l > 0 ? p.mlp_out : nullptr;
+                ga.gemm_out = nullptr;
+                if (l > 0) {
+                    ga.acc = p.fc2_acc + (size_t)((l - 1) & 1) * MAXM * h;
+                    ga.acc_bias = static_cast<const bf16*>(Lp.b_fc2);
+                }
                 ga.g_post = static_cast<const bf16*>(Lp.ln4_g); ga.b_post = static_cast<const bf16*>(Lp.ln4_b);
                 ga.res_in = p.resid_a; ga.res_out = p.resid_b;
                 ga.g_pre = static_cast<const bf16*>(Lw.ln1_g); ga.b_pre = static_cast<const bf16*>(Lw.ln1_b);
@@ -659,8 +786,12 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
         }
         // ---- activation operand written by other CTAs ----
         if (!fin && (phs == 2 || phs == 4)) {
-            if (phs == 2) load_x(p.ctx, h, 0);
-            else load_x(p.h4, 4 * h, kg * h);
+            if (phs == 2) {
+                if (l > 0) zero_acc(p.fc2_acc + (size_t)((l - 1) & 1) * MAXM * h);   // read by every CTA in phase 0
+                load_x(p.ctx, h, 0);
+            } else {
+                load_x(p.h4, 4 * h, kg * h);
+            }
         }
         // ---- the phase's work ----
         if (!fin && phs == 1) {
@@ -681,11 +812,10 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
                 m = make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0); epi = EPI_BF16_GELU; bias = static_cast<const bf16*>(Lw.b_fc1);
                 out = p.h4; ldo = 4 * h;
             } else {
-                m = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, rg, G / KG, kg * h); epi = EPI_F32;
-                out = p.fc2_part + (size_t)kg * MAXM * h;
+                m = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, rg, G / KG, kg * h); epi = EPI_FIX64;
+                out = p.fc2_acc + (size_t)(l & 1) * MAXM * h;
             }
             consume(m, epi, bias, out, ldo);
-            if (!fin && phs == 4) fc2_merge(m, rg, static_cast<const bf16*>(Lw.b_fc2));
         }
         if (!fin) {
             const int after_work = phs == 0 ? 2 : (phs == 1 ? 4 : (phs == 2 ? 6 : (phs == 3 ? 9 : 11)));
@@ -705,7 +835,7 @@ constexpr size_t WS_DATA = 8192;
 inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct WsLayout {
-    size_t qkv, ctx, attn_out, h4, mlp_out, resid_a, resid_b, fc2_part, attn_part, total;
+    size_t qkv, ctx, attn_out, h4, mlp_out, resid_a, resid_b, fc2_acc, attn_part, total;
 };
 WsLayout ws_layout(int h, int heads) {
     WsLayout w;
@@ -717,8 +847,8 @@ WsLayout ws_layout(int h, int heads) {
     w.mlp_out = o; o += al256((size_t)MAXM * h * 2);
     w.resid_a = o; o += al256((size_t)MAXM * h * 4);
     w.resid_b = o; o += al256((size_t)MAXM * h * 4);
-    w.fc2_part = o; o += al256((size_t)KG * MAXM * h * 4);
-    w.attn_part = o; o += al256((size_t)MAXM * heads * 16 * PART_STRIDE * 4);
+    w.fc2_acc = o; o += al256((size_t)2 * MAXM * h * 8);
+    w.attn_part = o; o += al256((size_t)MAXM * heads * KVB_MAX * PART_STRIDE * 4);
     w.total = o;
     return w;
 }
@@ -744,6 +874,11 @@ extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
     CV_REQUIRE(h > 0 && h % 256 == 0 && h <= 2560, "hidden must be a multiple of 256 and <= 2560");
     CV_REQUIRE(heads > 0 && heads * HD == h && heads <= (1024 / MAXM), "hidden must be heads * 64");
     CV_REQUIRE(a->num_layers >= 1 && a->vocab >= 1 && a->max_len >= 1 && a->ld_logits >= a->vocab, "bad sizes");
+    CV_REQUIRE(a->max_len <= KVB * KVB_MAX, "max_len must be <= 4096");
+    CV_REQUIRE(a->cache_batch_stride == (int64_t)a->max_len * 2 * h &&
+                   a->cache_layer_stride == (int64_t)M * a->max_len * 2 * h &&
+                   (reinterpret_cast<uintptr_t>(a->cache) & 15) == 0,
+               "the K|V cache must be a contiguous [layers, batch, max_len, 2*hidden] bf16 tensor");
     CV_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = step_grid();
@@ -765,13 +900,12 @@ extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
     p.bar_ctr = reinterpret_cast<unsigned long long*>(ws + WS_CTR);
     p.bar_base = p.bar_ctr + 1;
     p.err = reinterpret_cast<int*>(ws + WS_CTR + 16);
-    p.fc2_cnt = reinterpret_cast<unsigned int*>(ws + WS_FC2CNT);
     p.attn_cnt = reinterpret_cast<unsigned int*>(ws + WS_ATTNCNT);
     p.qkv = reinterpret_cast<bf16*>(ws + w.qkv); p.ctx = reinterpret_cast<bf16*>(ws + w.ctx);
     p.attn_out = reinterpret_cast<bf16*>(ws + w.attn_out); p.h4 = reinterpret_cast<bf16*>(ws + w.h4);
     p.mlp_out = reinterpret_cast<bf16*>(ws + w.mlp_out);
     p.resid_a = reinterpret_cast<float*>(ws + w.resid_a); p.resid_b = reinterpret_cast<float*>(ws + w.resid_b);
-    p.fc2_part = reinterpret_cast<float*>(ws + w.fc2_part); p.attn_part = reinterpret_cast<float*>(ws + w.attn_part);
+    p.fc2_acc = reinterpret_cast<long long*>(ws + w.fc2_acc); p.attn_part = reinterpret_cast<float*>(ws + w.attn_part);
 
     // stage = 16 weight rows x kstage columns; kstage = the largest multiple of 256 dividing h that is <= 1280
     int kstage = 256;
@@ -803,7 +937,17 @@ extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
     p.S = S;
     p.scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
 
-    typedef void (*KernelFn)(const Params);
+    // K|V cache as a 4-D tensor: [2h | max_len | batch | layer], boxes of [64 dims x KVB keys] (one head's K or V)
+    alignas(64) CUtensorMap tmKV;
+    {
+        const uint64_t dims[4] = {(uint64_t)2 * h, (uint64_t)a->max_len, (uint64_t)M, (uint64_t)a->num_layers};
+        const uint64_t str[3] = {(uint64_t)2 * h * 2, (uint64_t)a->cache_batch_stride * 2, (uint64_t)a->cache_layer_stride * 2};
+        const uint32_t box[4] = {HD, KVB, 1, 1};
+        int rc = cvh::encode_tmap(&tmKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->cache, dims, str, box, nullptr,
+                                  cvh::Swizzle::None);
+        if (rc) return rc;
+    }
+    typedef void (*KernelFn)(const Params, const CUtensorMap);
     KernelFn fn = nullptr;
     const int cpw = kstage / 256;
 #define DS_PICK(MR_)                                                    \
@@ -834,7 +978,7 @@ extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = coop ? 1 : 0;
-    CV_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
+    CV_CUDA(cudaLaunchKernelEx(&cfg, fn, p, tmKV));
     cvh::count_launches(1);
     return 0;
 }
