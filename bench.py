@@ -298,7 +298,14 @@ def run_train(args, cfg, world, rank, dev_index, steps, warmup):
         g.setdefault("weight_decay", 0.01)
     opt = FusedAdamW(groups, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0)
     net = model
+    reserved = 0
     if world > 1:
+        # the gradient all-reduce (pretrain_gpt2.py:99-105) runs as NCCL kernels NEXT TO the backward GEMMs: keep a few
+        # SMs out of the persistent GEMM grid for them (a grid sized to all 148 SMs would find some taken and run a
+        # second, nearly empty wave), and cap NCCL's CTAs to what was reserved (main() sets NCCL_MAX_CTAS)
+        from cogview_b200 import _lib
+        reserved = int(os.environ.get("COGVIEW_B200_RESERVE_SMS", "16"))
+        _lib.lib().cv_set_reserved_sms(reserved)
         net = PyTorchDistributedDataParallel(model, device_ids=[torch.cuda.current_device()],
                                              gradient_as_bucket_view=True, bucket_cap_mb=200)
     b, s = args.batch, cfg["max_sequence_length"] - 1
@@ -354,6 +361,10 @@ def run_train(args, cfg, world, rank, dev_index, steps, warmup):
                roofline_step=dict(bound="tensor", achieved=achieved, peak=pk["tf_sust"], unit="TFLOP/s",
                                   frac=achieved / pk["tf_sust"], peak_source=pk["src"],
                                   note="whole step (all kernels) vs sustained cuBLAS bf16 peak"))
+    res["config"]["reserved_sms_for_nccl"] = reserved
+    if world > 1:
+        from cogview_b200 import _lib
+        _lib.lib().cv_set_reserved_sms(0)
     res["roofline"] = gemm_roofline(cfg, b * s)
     del net, model, opt
     torch.cuda.empty_cache()
@@ -769,6 +780,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("COGVIEW_B200_RESERVE_SMS", "16"))
         torch.distributed.init_process_group("nccl")
         from cogview_b200 import mpu
         mpu.initialize_model_parallel(1)

@@ -92,6 +92,8 @@ def _declare(lib):
     lib.cv_attn_decode_workspace_bytes.argtypes = [I, I, I]
     lib.cv_attn_decode_workspace_bytes.restype = L
     lib.cv_launch_count.restype = ctypes.c_longlong
+    lib.cv_set_reserved_sms.argtypes = [I]
+    lib.cv_set_reserved_sms.restype = I
     lib.cv_colsum_workspace_bytes.argtypes = [I]
     lib.cv_colsum_workspace_bytes.restype = L
     for name, args in sigs.items():

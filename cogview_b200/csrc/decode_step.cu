@@ -74,7 +74,7 @@ struct Params {
     int* err;
     unsigned long long* prof;      // optional [grid][L][16] globaltimer stamps of the phase boundaries
     // derived on the host
-    int kstage, nst, stage_bytes, pitch, xpitch, S, quiet;
+    int kstage, nst, stage_bytes, pitch, xpitch, S, quiet, pf_stages;
     float scale_log2;
 };
 
@@ -108,6 +108,15 @@ __device__ __forceinline__ void tma_load_4d_u32(uint32_t dst, const CUtensorMap*
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint64_t evict_first_policy() {
     uint64_t pol;
@@ -190,58 +199,119 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
     // ============================================================================================
     if (warp == CW) {
         const uint64_t pol = evict_first_policy();
-        int st = 0;
-        uint32_t ph = 0;
-        auto produce = [&](const Mat& m) {
-            for (int r = m.r0; r < m.r1; r += TILE) {
-                const int rows = min(TILE, m.r1 - r);
-                for (int ks = 0; ks < nks; ++ks) {
-                    mbar_wait(&empty[st], ph ^ 1);
-                    if (p.quiet) {      // experiment: no weight traffic while the consumers are in a latency phase
-                        while (*reinterpret_cast<volatile int*>(&flags[1]) != 0) __nanosleep(64);
-                    }
-                    if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)(rows * p.kstage * 2));
-                    __syncwarp();
-                    if (lane < rows)
-                        bulk_g2s(ring + st * p.stage_bytes + lane * p.pitch,
-                                 m.W + (size_t)(r + lane) * m.ldw + m.k0 + ks * p.kstage, (uint32_t)(p.kstage * 2),
-                                 smem_u32(&full[st]), pol);
-                    if (++st == p.nst) { st = 0; ph ^= 1; }
+        const int t_p = __ldg(p.cur_len);
+        const int nblk_p = (t_p + KVB - 1) / KVB;
+        const long long NBp = (long long)p.M * p.heads * nblk_p;
+        const int kf0 = (int)((NBp * cta) / G), kf1 = (int)((NBp * (cta + 1)) / G);
+        // The CTA's static schedule as a cursor over ring stages: per layer the QKV matrix, the CTA's K|V key blocks,
+        // dense, h->4h, 4h->h; then the vocabulary matrix.  Two cursors walk it: `ld` feeds the ring, `pf` runs
+        // pf_stages further ahead and only pulls the bytes into L2 (cp.async.bulk.prefetch.L2) — when the consumers
+        // come out of a grid barrier / glue / attention gap longer than the ring covers, they catch up from L2 (2-3x
+        // the HBM rate) while the HBM stream itself never stopped.
+        struct Cur {
+            int it, r, ks, f;
+            bool kv, done;
+            Mat m;
+        };
+        auto set_mat = [&](Cur& c) {
+            const int l = c.it >> 2, which = c.it & 3;
+            if (c.it >= 4 * p.L) {
+                c.m = make_mat(p.wte, h, p.V, cta, G, 0);
+            } else {
+                const cv_decode_layer& Lw = p.layers[l];
+                if (which == 0) c.m = make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0);
+                else if (which == 1) c.m = make_mat(Lw.w_dense, h, h, cta, G, 0);
+                else if (which == 2) c.m = make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0);
+                else c.m = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, cta / KG, G / KG, (cta % KG) * h);
+            }
+            c.r = c.m.r0;
+            c.ks = 0;
+        };
+        auto normalize = [&](Cur& c) {                     // point at an existing stage, or done
+            while (!c.done) {
+                if (c.kv) {
+                    if (c.f < kf1) return;
+                    c.kv = false;
+                    ++c.it;
+                    set_mat(c);
+                } else if (c.r < c.m.r1) {
+                    return;
+                } else if (c.it < 4 * p.L && (c.it & 3) == 0) {
+                    c.kv = true;                           // K|V blocks of this layer follow its QKV weights
+                    c.f = kf0;
+                } else if (c.it >= 4 * p.L) {
+                    c.done = true;
+                } else {
+                    ++c.it;
+                    set_mat(c);
                 }
             }
         };
-        for (int it = 0; it <= 4 * p.L; ++it) {       // one call site (instruction-cache footprint)
-            const int l = it >> 2, which = it & 3;
-            Mat m;
-            if (it == 4 * p.L) {
-                m = make_mat(p.wte, h, p.V, cta, G, 0);
-            } else {
-                const cv_decode_layer& Lw = p.layers[l];
-                if (which == 0) m = make_mat(Lw.w_qkv, h, 3 * h, cta, G, 0);
-                else if (which == 1) m = make_mat(Lw.w_dense, h, h, cta, G, 0);
-                else if (which == 2) m = make_mat(Lw.w_fc1, h, 4 * h, cta, G, 0);
-                else m = make_mat(Lw.w_fc2, 4 * (int64_t)h, h, cta / KG, G / KG, (cta % KG) * h);
+        auto step = [&](Cur& c) {
+            if (c.kv) {
+                ++c.f;
+            } else if (++c.ks == nks) {
+                c.ks = 0;
+                c.r += TILE;
             }
-            produce(m);
-            if (it < 4 * p.L && which == 0) {             // this CTA's K|V key blocks of layer l follow its QKV weights
-                const int t = __ldg(p.cur_len);
-                const int nblk = (t + KVB - 1) / KVB;
-                const long long NBt = (long long)p.M * p.heads * nblk;
-                const int f0 = (int)((NBt * cta) / G), f1 = (int)((NBt * (cta + 1)) / G);
-                for (int f = f0; f < f1; ++f) {
-                    const int bh = f / nblk, blk = f - bh * nblk;
-                    const int head = bh % p.heads, batch = bh / p.heads;
-                    mbar_wait(&empty[st], ph ^ 1);
-                    if (lane == 0) {
-                        mbar_expect_tx(&full[st], 2 * KVB * 128);
-                        const uint32_t dst = ring + st * p.stage_bytes;
-                        tma_load_4d_u32(dst, &tmKV, smem_u32(&full[st]), head * HD, blk * KVB, batch, l);
-                        tma_load_4d_u32(dst + KVB * 128, &tmKV, smem_u32(&full[st]), h + head * HD, blk * KVB, batch, l);
+            normalize(c);
+        };
+        auto issue = [&](const Cur& c, bool prefetch, int slot) {
+            if (c.kv) {
+                const int bh = c.f / nblk_p, blk = c.f - bh * nblk_p;
+                const int head = bh % p.heads, batch = bh / p.heads, l = c.it >> 2;
+                if (lane == 0) {
+                    if (prefetch) {
+                        tma_prefetch_4d(&tmKV, head * HD, blk * KVB, batch, l);
+                        tma_prefetch_4d(&tmKV, h + head * HD, blk * KVB, batch, l);
+                    } else {
+                        mbar_expect_tx(&full[slot], 2 * KVB * 128);
+                        const uint32_t dst = ring + slot * p.stage_bytes;
+                        tma_load_4d_u32(dst, &tmKV, smem_u32(&full[slot]), head * HD, blk * KVB, batch, l);
+                        tma_load_4d_u32(dst + KVB * 128, &tmKV, smem_u32(&full[slot]), h + head * HD, blk * KVB, batch, l);
                     }
+                }
+                __syncwarp();
+            } else {
+                const int rows = min(TILE, c.m.r1 - c.r);
+                const bf16* src = c.m.W + (size_t)(c.r + lane) * c.m.ldw + c.m.k0 + c.ks * p.kstage;
+                if (prefetch) {
+                    if (lane < rows) bulk_prefetch_l2(src, (uint32_t)(p.kstage * 2));
+                } else {
+                    if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)(rows * p.kstage * 2));
                     __syncwarp();
-                    if (++st == p.nst) { st = 0; ph ^= 1; }
+                    if (lane < rows)
+                        bulk_g2s(ring + slot * p.stage_bytes + lane * p.pitch, src, (uint32_t)(p.kstage * 2),
+                                 smem_u32(&full[slot]), pol);
                 }
             }
+        };
+        Cur ld, pf;
+        ld.it = 0; ld.f = 0; ld.kv = false; ld.done = false;
+        set_mat(ld);
+        normalize(ld);
+        pf = ld;
+        int ahead = 0;                                     // stages between pf and ld
+        const int ahead_min = p.nst, ahead_max = p.nst + p.pf_stages;
+        if (p.pf_stages > 0)
+            for (; ahead < ahead_min && !pf.done; ++ahead) step(pf);    // the ring itself covers the first nst stages
+        int st = 0;
+        uint32_t ph = 0;
+        while (!ld.done) {
+            if (p.pf_stages > 0) {
+                for (; ahead < ahead_max && !pf.done; ++ahead) {
+                    issue(pf, true, 0);
+                    step(pf);
+                }
+            }
+            mbar_wait(&empty[st], ph ^ 1);
+            if (p.quiet) {      // experiment: no weight traffic while the consumers are in a latency phase
+                while (*reinterpret_cast<volatile int*>(&flags[1]) != 0) __nanosleep(64);
+            }
+            issue(ld, false, st);
+            step(ld);
+            --ahead;
+            if (++st == p.nst) { st = 0; ph ^= 1; }
         }
         return;
     }
@@ -571,12 +641,9 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
         const int f0 = (int)((NBt * cta) / G), f1 = (int)((NBt * (cta + 1)) / G);
         float* sm_acc = part;                                 // [CW][HD] warp states (aliases the tile partials)
         float* sm_ml = red;                                   // [CW][2]
-        auto lo_of = [&](int c) { return (int)((NBt * c) / G); };
-        auto owner = [&](int f) {
-            int c = (int)(((long long)f * G) / NBt);
-            while (lo_of(c + 1) <= f) ++c;
-            return c;
-        };
+        // CTA that owns flattened block f: the largest c with floor(NBt c / G) <= f  (32-bit: NBt G < 2^31)
+        const int nbt = (int)NBt;
+        auto owner = [&](int f) { return min(G - 1, ((f + 1) * G - 1) / nbt); };
         float qf[8], m = -INFINITY, lsum = 0.f, acc[8];
         int cur = -1;
         auto start_pair = [&](int bh) {
@@ -610,21 +677,20 @@ __global__ void __launch_bounds__(NT, 1) decode_step_kernel(const __grid_constan
         };
         auto finish_pair = [&](int bh) {
             const int head = bh % p.heads, batch = bh / p.heads;
-            // contributors of this pair = distinct owners of its key blocks (non-decreasing in the block index)
+            // contributors of this pair = the distinct owners of its key blocks.  With at least one block per CTA
+            // (nbt >= G) they are the consecutive CTAs first..last; otherwise every non-empty CTA owns exactly one block.
             int ncontrib = 1, my_idx = 0;
             bool owns_last = true;
             if (nblk > 0) {
-                int prev = -1;
-                ncontrib = 0;
-                for (int bq = 0; bq < nblk; ++bq) {
-                    const int o = owner(bh * nblk + bq);
-                    if (o != prev) {
-                        if (o == cta) my_idx = ncontrib;
-                        ++ncontrib;
-                        prev = o;
-                    }
+                const int cf = owner(bh * nblk), cl = owner(bh * nblk + nblk - 1);
+                owns_last = cl == cta;
+                if (nbt >= G) {
+                    ncontrib = cl - cf + 1;
+                    my_idx = cta - cf;
+                } else {
+                    ncontrib = nblk;
+                    my_idx = f0 - bh * nblk;            // this CTA's single block
                 }
-                owns_last = prev == cta;
             }
             if (owns_last && warp == 0) {                     // the new token: key index t, K/V from the QKV output
                 const bf16* qrow = p.qkv + (size_t)batch * 3 * h + head * HD + sub * 8;
@@ -928,6 +994,11 @@ extern "C" int cv_decode_step(const cv_decode_step_args* a, void* stream) {
     {
         const char* e = getenv("COGVIEW_B200_STEP_QUIET");
         p.quiet = (e && e[0] == '1') ? 1 : 0;
+        // L2 prefetch distance in ring stages beyond the ring (~41 KB each, x SMs): 10 -> ~60 MB of the 126 MB L2
+        const char* f = getenv("COGVIEW_B200_STEP_PF");
+        p.pf_stages = f ? atoi(f) : 10;
+        if (p.pf_stages < 0) p.pf_stages = 0;
+        if (p.pf_stages > 64) p.pf_stages = 64;
     }
     CV_REQUIRE(nst >= 2, "not enough shared memory for the weight ring");
     p.nst = nst;

@@ -361,7 +361,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
         attr_set = true;
     }
     int tiles = p.num_tiles;
-    int grid = tiles < cvh::num_sms() ? tiles : cvh::num_sms();
+    int grid = tiles < cvh::gemm_sms() ? tiles : cvh::gemm_sms();
     kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cvh::fail_cuda("cv_gemm_bf16", e);
@@ -416,7 +416,7 @@ static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, 
         // (measured: ~0.9 vs ~1.4 PFLOP/s): cost 192 vs 256 per tile.
         // With tail-wave splitting (tile_coord) the last partial wave of the 256-wide schedule costs one 128-wide
         // tile when its tiles fit twice on the SMs.
-        const int sms = cvh::num_sms();
+        const int sms = cvh::gemm_sms();
         const int mb = (M + BM - 1) / BM;
         const long t128 = (long)mb * ((N + 127) / 128), t256 = (long)mb * ((N + 255) / 256);
         const long cost128 = (t128 + sms - 1) / sms * 192;
@@ -432,7 +432,7 @@ static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, 
     p.num_n_blocks = (N + BN - 1) / BN;
     p.num_k_blocks = (K + BK - 1) / BK;
     {
-        const int tiles = p.num_m_blocks * p.num_n_blocks, sms = cvh::num_sms();
+        const int tiles = p.num_m_blocks * p.num_n_blocks, sms = cvh::gemm_sms();
         const int r = tiles % sms;
         const int nsplit = (BN == 256 && split_tail_enabled() && r > 0 && 2 * r <= sms) ? r : 0;
         p.split_from = tiles - nsplit;

@@ -51,6 +51,23 @@ int num_sms() {
     return n;
 }
 
+// SMs the persistent GEMM may occupy.  Under data parallelism the NCCL all-reduce kernels of the gradient buckets run
+// concurrently with the backward GEMMs; a persistent grid sized to ALL SMs then finds a few of them taken and runs a
+// second, nearly empty wave.  cv_set_reserved_sms(k) (or COGVIEW_B200_RESERVE_SMS) keeps k SMs free for them.
+static std::atomic<int> g_reserved{-1};
+int gemm_sms() {
+    int r = g_reserved.load(std::memory_order_relaxed);
+    if (r < 0) {
+        const char* e = getenv("COGVIEW_B200_RESERVE_SMS");
+        r = e ? atoi(e) : 0;
+        if (r < 0) r = 0;
+        g_reserved.store(r, std::memory_order_relaxed);
+    }
+    const int n = num_sms();
+    return r < n - 8 ? n - r : 8;
+}
+void set_reserved_sms(int k) { g_reserved.store(k < 0 ? 0 : k, std::memory_order_relaxed); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -113,5 +130,10 @@ const char* cv_last_error(void) { return cvh::last_error().c_str(); }
 int cv_version(void) { return CV_B200_VERSION; }
 
 long long cv_launch_count(void) { return cvh::launches(); }
+
+int cv_set_reserved_sms(int k) {
+    cvh::set_reserved_sms(k);
+    return cvh::gemm_sms();
+}
 
 }

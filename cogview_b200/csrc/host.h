@@ -51,6 +51,8 @@ inline HostDropout make_dropout(float p, uint64_t seed, uint32_t stream) {
 }
 
 int num_sms();
+int gemm_sms();               // num_sms() minus the SMs reserved for concurrently running collectives
+void set_reserved_sms(int k);
 void count_launches(int n);
 long long launches();   // kernels launched by this library since load (cv_launch_count)
 

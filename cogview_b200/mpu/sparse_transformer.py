@@ -143,6 +143,22 @@ _PARAM_ORDER = ('input_layernorm.weight', 'input_layernorm.bias',
                 'fourth_layernorm.weight', 'fourth_layernorm.bias')
 
 
+class SparseSpec:
+    """Attention pattern of sparse TRAINING (is_sparse == 1, mpu/sparse_transformer.py:675-725): takes the place of
+    the int `sep` in layer_forward / layer_backward.  pivot_idx: int64 [b, n_piv] on the device."""
+
+    def __init__(self, pivot_idx, query_window, key_window_times):
+        self.pivot_idx = pivot_idx.contiguous()
+        self.w = int(query_window)
+        self.times = int(key_window_times)
+
+
+def _no_sparse_dropout(drops):
+    if drops is not None and drops['attn'][0] > 0:
+        raise NotImplementedError('attention-probability dropout is not available with sparse training attention '
+                                  '(is_sparse=1): set attention_dropout_prob = 0')
+
+
 def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None, attn=None, drops=None):
     """One Sandwich-LN block (mpu/sparse_transformer.py:314-342) on the fp32 residual stream x [b*sq, h].
 
@@ -162,6 +178,12 @@ def layer_forward(x, am_x, P, heads, eps, b, sq, sep, kv=None, save=None, attn=N
         k, v = kv(k, v)
     if attn is not None:            # sparse inference: attention over a gathered key set
         ctx, lse = attn(q), None
+    elif isinstance(sep, SparseSpec):   # sparse training: causal band + gathered pivots, one softmax
+        _no_sparse_dropout(drops)
+        if training:
+            ctx, lse = ops.attn_sparse_fwd(q, k, v, heads, sep.pivot_idx, sep.w, sep.times, want_lse=True)
+        else:
+            ctx, lse = ops.attn_sparse_fwd(q, k, v, heads, sep.pivot_idx, sep.w, sep.times), None
     elif training and drops is not None and drops['attn'][0] > 0:
         ctx, lse, amask = ops.attn_fwd(q, k, v, heads, sep=sep, want_lse=True, dropout=drops['attn'])
         drops['attn_mask'] = amask
@@ -221,9 +243,13 @@ def layer_backward(d_out, saved, P, heads, b, sq, sep, drops=None):
     dbd = r3[3] if fuse_bias else ops.colsum(d_attn_out)
     qkv3 = qkv.view(b, sq, 3 * h)
     use_ad = bool(drops) and drops['attn'][0] > 0
-    d_qkv = ops.attn_bwd(qkv3[..., :h], qkv3[..., h:2 * h], qkv3[..., 2 * h:], ctx, d_ctx.view(b, sq, h), lse, heads,
-                         sep=sep, dropout_p=drops['attn'][0] if use_ad else 0.0,
-                         drop_mask=drops['attn_mask'] if use_ad else None)
+    if isinstance(sep, SparseSpec):
+        d_qkv = ops.attn_sparse_bwd(qkv3[..., :h], qkv3[..., h:2 * h], qkv3[..., 2 * h:], ctx, d_ctx.view(b, sq, h), lse,
+                                    heads, sep.pivot_idx, sep.w, sep.times)
+    else:
+        d_qkv = ops.attn_bwd(qkv3[..., :h], qkv3[..., h:2 * h], qkv3[..., 2 * h:], ctx, d_ctx.view(b, sq, h), lse, heads,
+                             sep=sep, dropout_p=drops['attn'][0] if use_ad else 0.0,
+                             drop_mask=drops['attn_mask'] if use_ad else None)
     d_qkv2 = d_qkv.view(M, 3 * h)
     d_ln1 = ops.gemm(d_qkv2, wqkv, b_mn_major=True)
     dwqkv = ops.gemm(d_qkv2, ln1, a_mn_major=True, b_mn_major=True)

@@ -28,6 +28,9 @@ int cv_version(void);
 const char* cv_last_error(void);
 /* number of kernels this library has launched since it was loaded (host-side counter) */
 long long cv_launch_count(void);
+/* Keep k SMs out of the persistent GEMM grid (returns the SMs it will use): under data parallelism the NCCL kernels of
+ * the gradient all-reduce (pretrain_gpt2.py:99-105) run next to the backward GEMMs and need somewhere to live. */
+int cv_set_reserved_sms(int k);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  C[M,N] = op(A)[M,K] * op(B)[N,K]^T (+ bias[N]) (+ tanh-GELU)      tcgen05 + TMA + TMEM
