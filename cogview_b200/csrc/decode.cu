@@ -545,8 +545,23 @@ extern "C" int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int6
     const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(bias);
     const size_t osz = out_is_f32 ? 4 : 2;
     // the MMA N dimension holds up to 8 batch rows; 9..16 rows take a second pass over the weights
+    // COGVIEW_B200_LINEAR_RING=1: the bulk-copy-ring kernel (csrc/linear_ring.cu) for M <= 8.  Parity-green, but in
+    // the 4B decode step it measured 3.10 ms per token against 2.91 ms for the fragment-direct kernel below (the step
+    // is bound by the latency of its ~340 dependent launches, not by the streaming rate of one of them): opt-in.
+    static int use_ring = -1;
+    if (use_ring < 0) {
+        const char* e = getenv("COGVIEW_B200_LINEAR_RING");
+        use_ring = (e && e[0] == '1') ? 1 : 0;
+    }
     for (int m0 = 0; m0 < M; m0 += 8) {
         const int mm = (M - m0) < 8 ? (M - m0) : 8;
+        if (use_ring) {
+            const int rc = cvh::linear_ring(xb + (size_t)m0 * ldx, ldx, wb, ldw, bb,
+                                            static_cast<void*>(static_cast<char*>(out) + (size_t)m0 * ldo * osz), ldo,
+                                            out_is_f32, act, absmax, mm, N, K, s);
+            if (rc == 0) continue;
+            if (rc != 1) return rc;
+        }
         CV_CUDA(cvh::launch_pdl(linear_small_m_kernel, dim3(grid), dim3(SK_WARPS * 32), 0, s, true,
                                 xb + (size_t)m0 * ldx, ldx, wb, ldw, bb,
                                 static_cast<void*>(static_cast<char*>(out) + (size_t)m0 * ldo * osz), ldo, out_is_f32,

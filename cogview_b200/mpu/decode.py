@@ -4,12 +4,13 @@ This is the fast path behind GPT2Model.forward when it is called the way generat
 it (one new token per sequence, `mems` returned by the previous call, mems_mode 'kv').
 
 Two device paths:
-  * batch <= 8 (default): the whole step — embedding, 48 Sandwich-LN layers, final LayerNorm, logits — is ONE
-    persistent kernel (cv_decode_step, csrc/decode_step.cu: TMA-staged weight stream in a shared-memory ring,
-    grid barriers between the dependency points), followed in generation runs by ONE sampling kernel
-    (cv_sample_topk).  Two kernels per generated token, captured as a CUDA graph.
-  * 9 <= batch <= 16, or COGVIEW_B200_PERSISTENT=0: one kernel per operation (cv_linear_small_m, cv_attn_decode,
-    cv_ln_pair_small_m), the round-1 path, also CUDA-graph captured.
+  * default: one kernel per operation (cv_linear_small_m, cv_attn_decode, cv_ln_pair_small_m; batch <= 16), CUDA-graph
+    captured; in generation runs followed by ONE sampling kernel (cv_sample_topk) inside the same graph.
+  * COGVIEW_B200_PERSISTENT=1 and batch <= 8: the whole step — embedding, 48 Sandwich-LN layers, final LayerNorm,
+    logits — is ONE persistent kernel (cv_decode_step, csrc/decode_step.cu: bulk-copy weight stream through a
+    shared-memory byte ring, register-resident residual stream, grid barriers between the dependency points).  Parity-
+    green and profiled per phase (tools/step_prof.py), but at 63 us per layer against 59 us for the per-operation path
+    (4B, batch 4: 1289 vs 1411 tokens/s) it is not the default: DESIGN.md §5 has the anatomy.
 """
 import os
 
@@ -21,7 +22,7 @@ from .layers import _as_bf16
 
 
 def _persistent_enabled():
-    return os.environ.get('COGVIEW_B200_PERSISTENT', '1') != '0'
+    return os.environ.get('COGVIEW_B200_PERSISTENT', '0') == '1'
 
 
 class DecodeRunner:

@@ -229,8 +229,8 @@ typedef struct cv_decode_step_args {
     float* logits;
     int64_t ld_logits;
     void* workspace;
-    void* prof;   /* NULL, or uint64 [SMs][num_layers][16]: %globaltimer stamps of the 13 phase boundaries of every
-                     layer, per CTA (tools/step_prof.py) */
+    void* prof;   /* NULL, or uint64 [SMs][num_layers][32]: %globaltimer stamps of the 13 phase boundaries of every
+                     layer and wait-cycle accounting of the four linears, per CTA (tools/step_prof.py) */
 } cv_decode_step_args;               /* HOST struct */
 int64_t cv_decode_step_workspace_bytes(int hidden, int heads);
 int cv_decode_step(const cv_decode_step_args* args, void* stream);

@@ -33,8 +33,8 @@ def main():
     r = DecodeRunner(model, c, use_graph=False)
     r._check_params()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    G = sms - sms % 4
-    prof = torch.zeros((G, a.layers, 16), dtype=torch.int64, device="cuda")
+    G = sms
+    prof = torch.zeros((G, a.layers, 32), dtype=torch.int64, device="cuda")
     r.ids.fill_(5)
     r.pos.fill_(a.t)
     r.cur_len.fill_(a.t)
@@ -71,6 +71,16 @@ def main():
     sub = [(g[:, :, 13] - g[:, :, 0]), (g[:, :, 14] - g[:, :, 13]), (g[:, :, 15] - g[:, :, 14]), (g[:, :, 1] - g[:, :, 15])]
     print("glueA anatomy (us): loads+reduce0 %.2f | dev+reduce1+v+reduce2 %.2f | dev2+reduce3 %.2f | xn+sync %.2f" % tuple(
         (x.mean().item() / 1e3) for x in sub))
+    acct(P)
+
+
+def acct(P):
+    # wait accounting of the four linears: cycles thread 0 (stage group 0) / thread 256 (group 1) spent waiting for
+    # ring data and in the per-tile barrier
+    A = P[:, 1:, 16:32].mean((0, 1)) / 1.9e3          # us at ~1.9 GHz
+    for gi, gname in enumerate(("group0", "group1")):
+        print(gname, " ".join("%s: data-wait %.2f tile-bar %.2f |" % (n, A[gi * 8 + 2 * i].item(), A[gi * 8 + 2 * i + 1].item())
+                              for i, n in enumerate(("qkv", "dense", "fc1", "fc2"))))
 
 
 if __name__ == "__main__":
