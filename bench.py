@@ -302,9 +302,11 @@ def run_train(args, cfg, world, rank, dev_index, steps, warmup):
     if world > 1:
         # the gradient all-reduce (pretrain_gpt2.py:99-105) runs as NCCL kernels NEXT TO the backward GEMMs: keep a few
         # SMs out of the persistent GEMM grid for them (a grid sized to all 148 SMs would find some taken and run a
-        # second, nearly empty wave), and cap NCCL's CTAs to what was reserved (main() sets NCCL_MAX_CTAS)
+        # second, nearly empty wave), and cap NCCL's CTAs to what was reserved (main() sets NCCL_MAX_CTAS).  Measured at
+        # N = 2 (4 x 1088 tokens per GPU): 182.4 ms with nothing reserved (NCCL up to 32 CTAs), 183.0 ms with 16, 180.1 ms
+        # with 8 (N = 1: 166.9 ms) — profiles/r02_train_2gpu_reserved_sms.txt
         from cogview_b200 import _lib
-        reserved = int(os.environ.get("COGVIEW_B200_RESERVE_SMS", "16"))
+        reserved = int(os.environ.get("COGVIEW_B200_RESERVE_SMS", "8"))
         _lib.lib().cv_set_reserved_sms(reserved)
         net = PyTorchDistributedDataParallel(model, device_ids=[torch.cuda.current_device()],
                                              gradient_as_bucket_view=True, bucket_cap_mb=200)
@@ -780,7 +782,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("COGVIEW_B200_RESERVE_SMS", "16"))
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("COGVIEW_B200_RESERVE_SMS", "8"))
         torch.distributed.init_process_group("nccl")
         from cogview_b200 import mpu
         mpu.initialize_model_parallel(1)

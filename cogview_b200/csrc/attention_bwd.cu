@@ -31,7 +31,7 @@ constexpr int QDO_STAGES = 2;
 constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + QDO_STAGES * 2 * TILE_BYTES /*Q,dO*/ + 2 * PT_BYTES /*P^T,dS^T*/ +
                            QDO_STAGES * 3 * BLK * 4 /*lse2, D, band start*/ + 1024 + 256;
 enum { MODE_DENSE = 0, MODE_BAND = 1, MODE_PIVOT = 2 };
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;     // TMA warp, MMA warp, 8 compute warps (two threads per key row)
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct BwdParams {
@@ -108,10 +108,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(kv_full, 1);
         for (int i = 0; i < QDO_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
         mbar_init(sdp_full, 1);
-        mbar_init(pds_full, 128);
+        mbar_init(pds_full, 256);
         mbar_init(pds_free, 1);
         mbar_init(dq_full, 1);
-        mbar_init(dq_free, 128);
+        mbar_init(dq_free, 256);
         fence_barrier_init();
     }
     if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
@@ -193,10 +193,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
     } else {
+        // 8 warps: warp w works on TMEM lane quadrant w % 4 (key rows 32 (w % 4) .. +31, one per lane); warps 2-5 take
+        // query columns 0-63 of every tile (and dQ / dK), warps 6-9 columns 64-127 (and dV): the per-tile chain of a
+        // thread is halved and every scheduler has two of these warps to overlap.  No exchange is needed between the two
+        // threads of a row — lse, delta and the band starts come from shared memory.
         const int q = warp_idx & 3;
+        const int hf = (warp_idx - 2) >> 2;
         const int row = q * 32 + lane;             // key row within the block
         const int kj = k0 + row;
-        const int epi_tid = threadIdx.x - 64;
+        const int epi_tid = threadIdx.x - 64;      // 0..255; the first 128 stage the per-query statistics
         const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
         const float masked_val = -10000.0f * LOG2E;
         const int my_pos = (MODE == MODE_PIVOT) ? (kj < p.sk ? p.piv_pos[(size_t)batch * p.sk + kj] : 0x7fffffff) : 0;
@@ -206,7 +211,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float pre_lse, pre_delta;
         uint4 pre_keep = make_uint4(0, 0, 0, 0);
         {
-            const int qn = i_start * BLK + epi_tid;
+            const int qn = i_start * BLK + (epi_tid & (BLK - 1));
             pre_lse = (qn < p.s) ? p.lse[stat_base + qn] * LOG2E : 0.f;
             pre_delta = (qn < p.s) ? p.delta[stat_base + qn] : 0.f;
             if (p.drop_mask != nullptr)
@@ -216,19 +221,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int q0 = (i_start + t) * BLK;
             // lse (log2 domain), delta and keep bits of this query block were fetched one tile ahead (registers):
             // publish them, then start the fetch for the next tile so its global-load latency is off the critical path
-            sLse[stage * BLK + epi_tid] = pre_lse;
-            sDelta[stage * BLK + epi_tid] = pre_delta;
-            if (MODE != MODE_DENSE) sBand[stage * BLK + epi_tid] = band_start(q0 + epi_tid, p.sp_w, p.sp_times);
+            if (hf == 0) {
+                sLse[stage * BLK + epi_tid] = pre_lse;
+                sDelta[stage * BLK + epi_tid] = pre_delta;
+                if (MODE != MODE_DENSE) sBand[stage * BLK + epi_tid] = band_start(q0 + epi_tid, p.sp_w, p.sp_times);
+            }
             const uint4 kw = pre_keep;                  // this key's keep bits over the 128 queries of the tile
             if (t + 1 < ntiles) {
-                const int qn = q0 + BLK + epi_tid;
+                const int qn = q0 + BLK + (epi_tid & (BLK - 1));
                 pre_lse = (qn < p.s) ? p.lse[stat_base + qn] * LOG2E : 0.f;
                 pre_delta = (qn < p.s) ? p.delta[stat_base + qn] : 0.f;
                 if (p.drop_mask != nullptr)
                     pre_keep = *reinterpret_cast<const uint4*>(p.drop_mask +
                                                                ((keep_base + kj) * (size_t)nqb + i_start + t + 1) * 4);
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             mbar_wait(sdp_full, t & 1);
             tc_fence_after();
             if (t > 0) mbar_wait(pds_free, (t - 1) & 1);   // MMAs of the previous tile no longer read P^T / dS^T
@@ -245,7 +252,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint8_t* prow = sPT + row * 128;
             uint8_t* drow = sDST + row * 128;
 #pragma unroll 2
-            for (int c = 0; c < BLK / 32; ++c) {
+            for (int c = hf * 2; c < hf * 2 + 2; ++c) {      // this thread's 64 query columns
                 uint32_t sr[32], dr[32];
                 tmem_ld_x32(lane_addr + TM_ST + c * 32, sr);
                 tmem_ld_x32(lane_addr + TM_DPT + c * 32, dr);
@@ -323,19 +330,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_wait(dq_full, t & 1);
             tc_fence_after();
             {
-                uint32_t r[HD];
-                uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-                uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-                tmem_ld_x32(lane_addr + TM_DQ, r0);
-                tmem_ld_x32(lane_addr + TM_DQ + 32, r1);
+                uint32_t r[HD / 2];                    // this thread's 32 of the row's 64 dims
+                tmem_ld_x32(lane_addr + TM_DQ + hf * (HD / 2), r);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(dq_free);
                 const int qi = q0 + row;               // here `row` indexes the query (dQ tile rows are queries)
                 if (qi < p.s) {
-                    float* dst = p.dq_acc + ((size_t)batch * p.s + qi) * (p.heads * HD) + head * HD;
+                    float* dst = p.dq_acc + ((size_t)batch * p.s + qi) * (p.heads * HD) + head * HD + hf * (HD / 2);
 #pragma unroll
-                    for (int i = 0; i < HD; i += 4)
+                    for (int i = 0; i < HD / 2; i += 4)
                         red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
                                    __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
                 }
@@ -350,8 +354,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int H3 = 3 * p.heads * HD;
             const bool row_ok = kj < p.kv_rows;
             __nv_bfloat16* base = p.dqkv + ((size_t)batch * p.kv_rows + (row_ok ? kj : 0)) * H3 + head * HD;
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
+            {
+                const int which = hf;                  // warps 2-5 store dK, warps 6-9 dV
                 uint32_t r[HD];
                 uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
                 uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);

@@ -12,11 +12,11 @@
 // Q, K, V are read in place from the packed QKV GEMM output [b, s, 3h] (or a KV cache) through 3-D TMA
 // tensor maps; the context is written token-major [b, sq, h] — the layout the out-projection GEMM reads.
 //
-// One CTA per (128-query block, head, batch); 6 warps:
+// One CTA per (128-query block, head, batch); 10 warps:
 //   warp 0     TMA producer (Q once; K/V tiles of 128 keys through a 3-stage ring)
 //   warp 1     tcgen05.mma issuer:  S = Q K^T (128x128x64) into TMEM;  O_j = P_j V_j (128x64x128) into TMEM
-//   warps 2-5  softmax: one thread per query row; tcgen05.ld S, online max/sum, P (bf16) -> swizzled smem,
-//              then accumulate O_j from TMEM into registers with the running rescale
+//   warps 2-9  softmax: two threads per query row (64 keys / 32 output dims each); tcgen05.ld S, online max/sum, P
+//              (bf16) -> swizzled smem, then accumulate O_j from TMEM into registers with the running rescale
 // S and O are double-buffered in TMEM so S_{j+1} is computed while the softmax of tile j runs.
 #include "common.cuh"
 #include "host.h"
@@ -33,8 +33,8 @@ constexpr int Q_BYTES = BQ * HD * 2;        // 16 KB
 constexpr int K_BYTES = BKV * HD * 2;       // 16 KB
 constexpr int V_BYTES = BKV * HD * 2;       // 16 KB
 constexpr int P_BYTES = BQ * BKV * 2;       // 32 KB (two 128x64 K-major sub-tiles)
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256 + 1024 /*sPos*/;
-constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256 + 1024 /*sPos*/ + 6 * BQ * 4 /*sX*/;
+constexpr int NUM_THREADS = 320;
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnParams {
@@ -86,6 +86,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* o_full = p_full + 2;           // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
     int* sPos = reinterpret_cast<int*>(bars + 32);           // [2][BKV] pivot positions of the current pivot tile
+    float* sX = reinterpret_cast<float*>(sPos + 2 * BKV);    // [2 tiles][2 halves][BQ] row maxima, [2][BQ] row sums
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // heaviest (last) query blocks first
@@ -114,7 +115,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_prefetch_desc(&tmV);
         mbar_init(q_full, 1);
         for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&o_full[i], 1); }
         fence_barrier_init();
     }
     if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
@@ -188,16 +189,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     } else {
         // ------------------------------ softmax / output warps ------------------------------
+        // 8 warps: warp w works on TMEM lane quadrant w % 4 (rows 32 (w % 4) .. +31, one row per lane) and on HALF of the
+        // row: warps 2-5 the first 64 keys of every tile and output dims 0-31, warps 6-9 the other half.  Two threads
+        // per row halve the serial exp2 / pack / rescale chain of a tile and give every scheduler two softmax warps to
+        // overlap (one warp per scheduler ran at 8 % tensor-pipe utilisation, profiles/r01_ncu_full_attention_summary);
+        // the only exchange per tile is the row maximum (shared memory + a 64-thread named barrier per quadrant).
         const int q = warp_idx & 3;
+        const int hf = (warp_idx - 2) >> 2;
         const int row = q * 32 + lane;
         const int qi = q0 + row;                       // query index within the sequence
         const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
         const int causal_lim = qi + p.off;             // last causally visible key
         const int bs_row = SPARSE ? band_start(qi, p.sp_w, p.sp_times) : 0;
+        constexpr int HK = BKV / 2, HO = HD / 2;       // keys / output dims per thread
         float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-        float o[HD];
+        float o[HO];
 #pragma unroll
-        for (int i = 0; i < HD; ++i) o[i] = 0.f;
+        for (int i = 0; i < HO; ++i) o[i] = 0.f;
         const float masked_val = -10000.0f * LOG2E;
         const uint4* keep_row = nullptr;
         uint4 pre_keep = make_uint4(0u, 0u, 0u, 0u);
@@ -209,38 +217,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
 
         for (int j = 0; j < nkb; ++j) {
-            uint4 kw = make_uint4(0u, 0u, 0u, 0u);      // keep bits of this row over the tile's 128 keys
+            uint32_t kw0 = 0u, kw1 = 0u;                // keep bits of this row over this thread's 64 keys
             if (DROPOUT) {
-                kw = pre_keep;
+                kw0 = hf ? pre_keep.z : pre_keep.x;
+                kw1 = hf ? pre_keep.w : pre_keep.y;
                 if (j + 1 < nkb) pre_keep = keep_row[j + 1];
             }
             const bool piv_tile = SPARSE && j >= nband;
             if (piv_tile) {                             // positions of this tile's 128 gathered keys -> shared memory
-                const int pj = (j - nband) * BKV + row;
-                sPos[(j & 1) * BKV + row] = pj < p.n_piv ? p.piv_pos[(size_t)batch * p.n_piv + pj] : 0x7fffffff;
-                named_bar_sync(2, 128);
+                if (hf == 0) {
+                    const int pj = (j - nband) * BKV + row;
+                    sPos[(j & 1) * BKV + row] = pj < p.n_piv ? p.piv_pos[(size_t)batch * p.n_piv + pj] : 0x7fffffff;
+                }
+                named_bar_sync(2, 256);
             }
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
             const int k0 = SPARSE ? (piv_tile ? (j - nband) * BKV : (jb0 + j) * BKV) : j * BKV;
+            const int kb = k0 + hf * HK;                // first key of this thread's half
             // does this tile need per-element masking for this row?
             const bool full_vis = SPARSE ? (!piv_tile && k0 >= bs_row && k0 + BKV - 1 <= qi && k0 + BKV <= p.sk)
                                          : (k0 + BKV <= p.sk) && ((k0 + BKV <= p.sep_eff) || (k0 + BKV - 1 <= causal_lim));
-            float s[BKV];
+            float s[HK];
 #pragma unroll
-            for (int c = 0; c < BKV / 32; ++c) {
+            for (int c = 0; c < HK / 32; ++c) {
                 uint32_t (&r)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
-                tmem_ld_x32(lane_addr + TM_S + (j & 1) * BKV + c * 32, r);
+                tmem_ld_x32(lane_addr + TM_S + (j & 1) * BKV + hf * HK + c * 32, r);
             }
             tmem_ld_wait();
-            float mx = m;
+            float mx = -INFINITY;
             if (full_vis) {
 #pragma unroll
-                for (int i = 0; i < BKV; ++i) { s[i] *= p.scale_log2; mx = fmaxf(mx, s[i]); }
+                for (int i = 0; i < HK; ++i) { s[i] *= p.scale_log2; mx = fmaxf(mx, s[i]); }
             } else if (piv_tile) {
-                const int* pos = sPos + (j & 1) * BKV;
+                const int* pos = sPos + (j & 1) * BKV + hf * HK;
 #pragma unroll
-                for (int i = 0; i < BKV; ++i) {
+                for (int i = 0; i < HK; ++i) {
                     const int pp = pos[i];
                     float v = pp < bs_row ? s[i] * p.scale_log2 + p.piv_bias_log2 : masked_val;
                     if (pp == 0x7fffffff) v = -INFINITY;   // beyond the pivot list
@@ -249,8 +261,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < BKV; ++i) {
-                    const int kj = k0 + i;
+                for (int i = 0; i < HK; ++i) {
+                    const int kj = kb + i;
                     const bool vis = SPARSE ? (kj >= bs_row && kj <= qi) : ((kj < p.sep_eff) || (kj <= causal_lim));
                     float v = vis ? s[i] * p.scale_log2 : masked_val;
                     if (kj >= p.sk) v = -INFINITY;     // key does not exist
@@ -258,12 +270,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     mx = fmaxf(mx, v);
                 }
             }
+            // row maximum over both halves
+            sX[((j & 1) * 2 + hf) * BQ + row] = mx;
+            named_bar_sync(3 + q, 64);
+            mx = fmaxf(fmaxf(mx, sX[((j & 1) * 2 + (hf ^ 1)) * BQ + row]), m);
             const float alpha = exp2f(m - mx);          // m = -inf on the first tile -> 0
             m = mx;
             float psum = 0.f;
-            uint8_t* prow = sP + (j & 1) * P_BYTES + row * 128;
+            uint8_t* prow = sP + (j & 1) * P_BYTES + hf * (BQ * 128) + row * 128;   // this half = one 64-key sub-tile
 #pragma unroll
-            for (int c = 0; c < BKV / 8; ++c) {         // 16 chunks of 8 keys (16 bytes)
+            for (int c = 0; c < HK / 8; ++c) {          // 8 chunks of 8 keys (16 bytes)
                 float e[8];
 #pragma unroll
                 for (int t = 0; t < 8; ++t) e[t] = exp2f(s[c * 8 + t] - mx);
@@ -276,32 +292,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int t = 0; t < 4; ++t) psum += __low2float(pb[t]) + __high2float(pb[t]);
                 if (DROPOUT) {   // dropout acts on the normalised probabilities: the row sum stays undropped; the
                                  // 1/(1-p) scale is applied once to the output row at the end
-                    const uint32_t w = (c >> 2) == 0 ? kw.x : ((c >> 2) == 1 ? kw.y : ((c >> 2) == 2 ? kw.z : kw.w));
+                    const uint32_t w = (c >> 2) == 0 ? kw0 : kw1;
 #pragma unroll
                     for (int t = 0; t < 8; ++t) e[t] = ((w >> ((c & 3) * 8 + t)) & 1u) ? e[t] : 0.f;
                     pk.x = pack_bf16x2(e[0], e[1]); pk.y = pack_bf16x2(e[2], e[3]);
                     pk.z = pack_bf16x2(e[4], e[5]); pk.w = pack_bf16x2(e[6], e[7]);
                 }
-                const int sub = c >> 3, cc = c & 7;     // sub-tile of 64 keys, 16-byte chunk within the 128 B row
-                *reinterpret_cast<uint4*>(prow + sub * (BQ * 128) + ((cc ^ (row & 7)) << 4)) = pk;
+                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = pk;
             }
-            l = l * alpha + psum;
+            l = l * alpha + psum;                       // this half's share of the row sum
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);
             if (j > 0) {
                 mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                uint32_t r[HD];
-                {
-                    uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-                    uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-                    tmem_ld_x32(lane_addr + TM_O + ((j - 1) & 1) * HD, r0);
-                    tmem_ld_x32(lane_addr + TM_O + ((j - 1) & 1) * HD + 32, r1);
-                }
+                uint32_t r[HO];
+                tmem_ld_x32(lane_addr + TM_O + ((j - 1) & 1) * HD + hf * HO, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < HD; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(r[i]);
+                for (int i = 0; i < HO; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(r[i]);
             }
             alpha_prev = alpha;
         }
@@ -309,22 +319,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int j = nkb - 1;
             mbar_wait(&o_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            uint32_t r[HD];
-            {
-                uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-                uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-                tmem_ld_x32(lane_addr + TM_O + (j & 1) * HD, r0);
-                tmem_ld_x32(lane_addr + TM_O + (j & 1) * HD + 32, r1);
-            }
+            uint32_t r[HO];
+            tmem_ld_x32(lane_addr + TM_O + (j & 1) * HD + hf * HO, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < HD; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(r[i]);
+            for (int i = 0; i < HO; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(r[i]);
         }
+        // total row sum = the two halves' shares
+        sX[(4 + hf) * BQ + row] = l;
+        named_bar_sync(3 + q, 64);
+        l += sX[(4 + (hf ^ 1)) * BQ + row];
         if (qi < p.sq) {
             const float inv_l = (DROPOUT ? p.drop.scale : 1.0f) / l;
-            __nv_bfloat16* orow = p.out + (size_t)batch * p.bso + (size_t)qi * p.ldo + head * HD;
+            __nv_bfloat16* orow = p.out + (size_t)batch * p.bso + (size_t)qi * p.ldo + head * HD + hf * HO;
 #pragma unroll
-            for (int c = 0; c < HD / 8; ++c) {
+            for (int c = 0; c < HO / 8; ++c) {
                 uint4 pk;
                 pk.x = pack_bf16x2(o[c * 8 + 0] * inv_l, o[c * 8 + 1] * inv_l);
                 pk.y = pack_bf16x2(o[c * 8 + 2] * inv_l, o[c * 8 + 3] * inv_l);
@@ -332,7 +341,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 pk.w = pack_bf16x2(o[c * 8 + 6] * inv_l, o[c * 8 + 7] * inv_l);
                 *reinterpret_cast<uint4*>(orow + c * 8) = pk;
             }
-            if (p.lse != nullptr)
+            if (hf == 0 && p.lse != nullptr)
                 p.lse[((size_t)batch * p.heads + head) * p.sq + qi] = m * 0.6931471805599453f + logf(l);
         }
     }

@@ -59,15 +59,20 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// WIDE: 9..16 rows of x — a second B fragment set (rows 8..15) and a second accumulator reuse the same weight
+// fragments, so the weights are still streamed ONCE (two passes of the 8-row kernel doubled the decode step time at
+// batch 16: 7.8 ms vs 3.8 ms at batch 8); half the K chunks in flight per warp keeps the register count.
+template <int UNROLL, bool WIDE>
 struct SkStage {
-    uint4 w0[SK_UNROLL], w1[SK_UNROLL], xv[SK_UNROLL];
+    uint4 w0[UNROLL], w1[UNROLL], xv[UNROLL], xw[WIDE ? UNROLL : 1];
 };
 
+template <int UNROLL, bool WIDE>
 __global__ void __launch_bounds__(SK_WARPS * 32, 2)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ W,
                       int64_t ldw, const __nv_bfloat16* __restrict__ bias, void* __restrict__ out, int64_t ldo,
                       int out_f32, int act, float* __restrict__ absmax, int M, int N, int K) {
-    __shared__ float part[2][SK_WARPS][SK_NT][8];
+    __shared__ float part[2][SK_WARPS][SK_NT][WIDE ? 16 : 8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     // Byte-balanced split: CTA i owns the contiguous output columns [N*i/G, N*(i+1)/G) — with G = 2 x SM count every
@@ -78,8 +83,9 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
     const int nchunks = (K + 31) / 32;
     const int per_warp = (nchunks + SK_WARPS - 1) / SK_WARPS;
     const int c_begin = warp * per_warp, c_end = min(nchunks, c_begin + per_warp);
-    const bool x_ok = g < M;
+    const bool x_ok = g < M, x2_ok = WIDE && g + 8 < M;
     const __nv_bfloat16* xrow = x + (size_t)g * ldx + q * 8;
+    const __nv_bfloat16* xrow2 = x + (size_t)(x2_ok ? g + 8 : g) * ldx + q * 8;
     const uint4 zero = make_uint4(0, 0, 0, 0);
     const uint64_t pol = make_evict_first_policy();
     float tmax = 0.f;
@@ -89,25 +95,26 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
         const bool r0_ok = n0 + g < c_hi, r1_ok = n0 + g + 8 < c_hi;
         const __nv_bfloat16* wrow0 = W + (size_t)(n0 + g) * ldw + q * 8;
         const __nv_bfloat16* wrow1 = W + (size_t)(n0 + g + 8) * ldw + q * 8;
-        auto load_w = [&](int c0, SkStage& st) {
+        auto load_w = [&](int c0, SkStage<UNROLL, WIDE>& st) {
 #pragma unroll
-            for (int u = 0; u < SK_UNROLL; ++u) {
+            for (int u = 0; u < UNROLL; ++u) {
                 const int c = c0 + u;
                 const bool in = c < c_end && c * 32 + q * 8 < K;
                 st.w0[u] = (in && r0_ok) ? ld_stream(wrow0 + (size_t)c * 32, pol) : zero;
                 st.w1[u] = (in && r1_ok) ? ld_stream(wrow1 + (size_t)c * 32, pol) : zero;
             }
         };
-        auto load_x = [&](int c0, SkStage& st) {
+        auto load_x = [&](int c0, SkStage<UNROLL, WIDE>& st) {
 #pragma unroll
-            for (int u = 0; u < SK_UNROLL; ++u) {
+            for (int u = 0; u < UNROLL; ++u) {
                 const int c = c0 + u;
                 const bool in = c < c_end && c * 32 + q * 8 < K;
                 st.xv[u] = (in && x_ok) ? *reinterpret_cast<const uint4*>(xrow + (size_t)c * 32) : zero;
+                if (WIDE) st.xw[u] = (in && x2_ok) ? *reinterpret_cast<const uint4*>(xrow2 + (size_t)c * 32) : zero;
             }
         };
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
-        SkStage st;
+        float d[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+        SkStage<UNROLL, WIDE> st;
         // weights do not depend on the previous kernel: request them, let the next kernel start its own prologue,
         // and only then wait for the producer of x
         load_w(c_begin, st);
@@ -119,16 +126,21 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
         load_x(c_begin, st);
         // rolling prefetch: slot u is refilled with chunk c + SK_UNROLL + u right after it has been consumed, so each
         // warp keeps SK_UNROLL chunks (512 B of each of its 16 weight rows) in flight from one register set
-        for (int c = c_begin; c < c_end; c += SK_UNROLL) {
+        for (int c = c_begin; c < c_end; c += UNROLL) {
 #pragma unroll
-            for (int u = 0; u < SK_UNROLL; ++u) {
+            for (int u = 0; u < UNROLL; ++u) {
                 mma_bf16_16816(d, st.w0[u].x, st.w1[u].x, st.w0[u].y, st.w1[u].y, st.xv[u].x, st.xv[u].y);
                 mma_bf16_16816(d, st.w0[u].z, st.w1[u].z, st.w0[u].w, st.w1[u].w, st.xv[u].z, st.xv[u].w);
-                const int cn = c + SK_UNROLL + u;
+                if (WIDE) {
+                    mma_bf16_16816(e, st.w0[u].x, st.w1[u].x, st.w0[u].y, st.w1[u].y, st.xw[u].x, st.xw[u].y);
+                    mma_bf16_16816(e, st.w0[u].z, st.w1[u].z, st.w0[u].w, st.w1[u].w, st.xw[u].z, st.xw[u].w);
+                }
+                const int cn = c + UNROLL + u;
                 const bool in = cn < c_end && cn * 32 + q * 8 < K;
                 st.w0[u] = (in && r0_ok) ? ld_stream(wrow0 + (size_t)cn * 32, pol) : zero;
                 st.w1[u] = (in && r1_ok) ? ld_stream(wrow1 + (size_t)cn * 32, pol) : zero;
                 st.xv[u] = (in && x_ok) ? *reinterpret_cast<const uint4*>(xrow + (size_t)cn * 32) : zero;
+                if (WIDE) st.xw[u] = (in && x2_ok) ? *reinterpret_cast<const uint4*>(xrow2 + (size_t)cn * 32) : zero;
             }
         }
         // D fragment: d0,d1 = (row g, cols 2q,2q+1), d2,d3 = (row g+8, cols 2q,2q+1); row = output column, col = m
@@ -136,8 +148,14 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
         part[buf][warp][g][2 * q + 1] = d[1];
         part[buf][warp][g + 8][2 * q] = d[2];
         part[buf][warp][g + 8][2 * q + 1] = d[3];
+        if (WIDE) {
+            part[buf][warp][g][8 + 2 * q] = e[0];
+            part[buf][warp][g][8 + 2 * q + 1] = e[1];
+            part[buf][warp][g + 8][8 + 2 * q] = e[2];
+            part[buf][warp][g + 8][8 + 2 * q + 1] = e[3];
+        }
         __syncthreads();
-        if (threadIdx.x < SK_NT * 8) {
+        if (threadIdx.x < SK_NT * (WIDE ? 16 : 8)) {
             const int m = threadIdx.x >> 4, nn = threadIdx.x & 15;   // consecutive threads -> consecutive columns
             float v = 0.f;
 #pragma unroll
@@ -161,7 +179,7 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
         pdl_launch_dependents();
         pdl_wait();
     }
-    if (absmax != nullptr && warp < 4) {
+    if (absmax != nullptr && warp < (WIDE ? 8 : 4)) {
         tmax = warp_max(tmax);
         if (lane == 0 && tmax > 0.f) atomic_max_nonneg(absmax, tmax);
     }
@@ -543,8 +561,13 @@ extern "C" int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int6
     const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
     const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(W);
     const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(bias);
-    const size_t osz = out_is_f32 ? 4 : 2;
-    // the MMA N dimension holds up to 8 batch rows; 9..16 rows take a second pass over the weights
+    // the MMA N dimension holds 8 batch rows: M <= 8 -> one B fragment set; 9..16 rows -> the WIDE kernel (two sets)
+    if (M > 8) {
+        CV_CUDA(cvh::launch_pdl(linear_small_m_kernel<SK_UNROLL / 2, true>, dim3(grid), dim3(SK_WARPS * 32), 0, s, true, xb,
+                                ldx, wb, ldw, bb, out, ldo, out_is_f32, act, absmax, M, N, K));
+        cvh::count_launches(1);
+        return 0;
+    }
     // COGVIEW_B200_LINEAR_RING=1: the bulk-copy-ring kernel (csrc/linear_ring.cu) for M <= 8.  Parity-green, but in
     // the 4B decode step it measured 3.10 ms per token against 2.91 ms for the fragment-direct kernel below (the step
     // is bound by the latency of its ~340 dependent launches, not by the streaming rate of one of them): opt-in.
@@ -553,21 +576,14 @@ extern "C" int cv_linear_small_m(const void* x, int64_t ldx, const void* W, int6
         const char* e = getenv("COGVIEW_B200_LINEAR_RING");
         use_ring = (e && e[0] == '1') ? 1 : 0;
     }
-    for (int m0 = 0; m0 < M; m0 += 8) {
-        const int mm = (M - m0) < 8 ? (M - m0) : 8;
-        if (use_ring) {
-            const int rc = cvh::linear_ring(xb + (size_t)m0 * ldx, ldx, wb, ldw, bb,
-                                            static_cast<void*>(static_cast<char*>(out) + (size_t)m0 * ldo * osz), ldo,
-                                            out_is_f32, act, absmax, mm, N, K, s);
-            if (rc == 0) continue;
-            if (rc != 1) return rc;
-        }
-        CV_CUDA(cvh::launch_pdl(linear_small_m_kernel, dim3(grid), dim3(SK_WARPS * 32), 0, s, true,
-                                xb + (size_t)m0 * ldx, ldx, wb, ldw, bb,
-                                static_cast<void*>(static_cast<char*>(out) + (size_t)m0 * ldo * osz), ldo, out_is_f32,
-                                act, absmax, mm, N, K));
-        cvh::count_launches(1);
+    if (use_ring) {
+        const int rc = cvh::linear_ring(xb, ldx, wb, ldw, bb, out, ldo, out_is_f32, act, absmax, M, N, K, s);
+        if (rc == 0) return 0;
+        if (rc != 1) return rc;
     }
+    CV_CUDA(cvh::launch_pdl(linear_small_m_kernel<SK_UNROLL, false>, dim3(grid), dim3(SK_WARPS * 32), 0, s, true, xb, ldx,
+                            wb, ldw, bb, out, ldo, out_is_f32, act, absmax, M, N, K));
+    cvh::count_launches(1);
     return 0;
 }
 

@@ -100,6 +100,75 @@ ln_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ absmax_in, co
     }
 }
 
+// Same operation with the row held in REGISTERS (cols <= 128 * NV): a lane issues all NV 16-byte loads of its row
+// before the first use, so 16 resident warps keep ~160 KB in flight per SM — the shared-memory staged kernel above has a
+// few loads in flight per warp and ran at 3.5 TB/s (111 MB in 31.4 us at the 4B shape, profiles/r01_train_step_launches_v3).
+template <typename TIn, typename TOut, bool RES, int NV>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+ln_fwd_reg_kernel(const TIn* __restrict__ x, const float* __restrict__ absmax_in, const __nv_bfloat16* __restrict__ gamma,
+                  const __nv_bfloat16* __restrict__ beta, float eps, const float* __restrict__ residual,
+                  TOut* __restrict__ out, float* __restrict__ absmax_out, float* __restrict__ mean_out,
+                  float* __restrict__ rstd_out, int rows, int cols) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float c = *absmax_in * 0.125f;
+    const float eps_eff = eps * c * c;
+    const float inv_n = 1.0f / cols;
+    float omax = 0.f;
+    for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
+        const TIn* xr = x + (size_t)row * cols;
+        float4 v[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = lane * 4 + j * 128;
+            v[j] = i < cols ? ld4(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        const float mean = warp_sum(s) * inv_n;
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (lane * 4 + j * 128 < cols) {
+                const float a = v[j].x - mean, b = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+                ss += (a * a + b * b) + (d * d + e * e);
+            }
+        }
+        const float var = warp_sum(ss) * inv_n;
+        const float rstd = rsqrtf(var + eps_eff);
+        if (lane == 0 && mean_out != nullptr) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+        TOut* orow = out + (size_t)row * cols;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = lane * 4 + j * 128;
+            if (i < cols) {
+                const float4 g = ld4(gamma + i), bt = ld4(beta + i);
+                float4 y;
+                y.x = (v[j].x - mean) * rstd * g.x + bt.x;
+                y.y = (v[j].y - mean) * rstd * g.y + bt.y;
+                y.z = (v[j].z - mean) * rstd * g.z + bt.z;
+                y.w = (v[j].w - mean) * rstd * g.w + bt.w;
+                if (RES) {
+                    const float4 r = ld4(residual + (size_t)row * cols + i);
+                    y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+                }
+                st4(orow + i, y);
+                if (absmax_out != nullptr) {
+                    omax = fmaxf(omax, fmaxf(fmaxf(fabsf(round_as(y.x, orow)), fabsf(round_as(y.y, orow))),
+                                             fmaxf(fabsf(round_as(y.z, orow)), fabsf(round_as(y.w, orow)))));
+                }
+            }
+        }
+    }
+    if (absmax_out != nullptr) {
+        omax = warp_max(omax);
+        if (lane == 0 && omax > 0.f) atomic_max_nonneg(absmax_out, omax);
+    }
+}
+
 // Backward.  dy: gradient of the LN output (TDy); dres (optional fp32): gradient already flowing on the
 // residual path that must be added to dx (fp32 output) — used for the input/post-attention/final LNs.
 //   dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)),  xhat = (x - mean) * rstd
@@ -328,8 +397,23 @@ extern "C" int cv_layernorm_absmax_fwd(const void* x, int x_is_bf16, const float
     const int grid = fwd_grid(rows);
     const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gamma);
     const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(beta);
+    static int reg_rows = -1;                            // COGVIEW_B200_LN_REG=0: the shared-memory staged kernel only
+    if (reg_rows < 0) {
+        const char* e = getenv("COGVIEW_B200_LN_REG");
+        reg_rows = (e && e[0] == '0') ? 0 : 1;
+    }
+    // measured at 4352 x 2560: 19.9 vs 21.5 us without the residual, 37.8 vs 33.7 us with it (tools/ln_time.py)
+    const bool use_reg = reg_rows && cols <= 128 * 20 && residual == nullptr;
+    int rgrid = 2 * cvh::num_sms();                      // two CTAs of 8 warps per SM, rows grid-strided
+    if (rgrid > (rows + WARPS - 1) / WARPS) rgrid = (rows + WARPS - 1) / WARPS;
 #define LAUNCH(TI, TO, RES)                                                                                    \
     do {                                                                                                       \
+        if (use_reg) {                                                                                         \
+            ln_fwd_reg_kernel<TI, TO, RES, 20><<<rgrid, WARPS * 32, 0, s>>>(                                   \
+                static_cast<const TI*>(x), absmax_in, g, b, eps, residual, static_cast<TO*>(out), absmax_out,  \
+                mean_out, rstd_out, rows, cols);                                                               \
+            break;                                                                                             \
+        }                                                                                                      \
         auto k = ln_fwd_kernel<TI, TO, RES>;                                                                   \
         CV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
         k<<<grid, WARPS * 32, smem, s>>>(static_cast<const TI*>(x), absmax_in, g, b, eps, residual,            \

@@ -239,7 +239,7 @@ def test_fused_adamw_matches_torch_adamw_on_fp32_masters(ops):
 
 
 @pytest.mark.parametrize("M,N,K,act", [(4, 7680, 2560, 0), (4, 2560, 10240, 0), (2, 1024, 256, 1), (1, 58240, 256, 0),
-                                       (8, 2560, 2560, 0), (13, 520, 264, 0)])
+                                       (8, 2560, 2560, 0), (13, 520, 264, 0), (16, 2560, 2560, 0), (9, 10240, 2560, 1)])
 def test_linear_small_m(ops, M, N, K, act):
     g = torch.Generator().manual_seed(M + N)
     x, w, bias = bf(torch.randn((M, K), generator=g)), bf(torch.randn((N, K), generator=g) * 0.05), bf(
