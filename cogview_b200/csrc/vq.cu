@@ -159,44 +159,69 @@ __global__ void im2col_k4s2_c3_kernel(const float* __restrict__ img, __nv_bfloat
     }
 }
 
-// out[b, c, y, x] = (sum_k x[(b,y,x), k] * w[c, k] + bias[c]) * scale[c] + shift[c];  one warp per 32 pixels
+// out[b, c, y, x] = (sum_k x[(b,y,x), k] * w[c, k] + bias[c]) * scale[c] + shift[c]   (the decoder's last 1x1 convolution,
+// vqvae/vqvae_zc.py:181-192, + the de-normalisation of api.code2img).  HBM bound: 2 cin bytes in, 12 bytes out per pixel.
+// 8 lanes per pixel, 4 pixels per warp: lane `sub` owns channels 8 sub + 64 j + t (t < 8), so the 8 lanes of a pixel read
+// 128 contiguous bytes per step and up to 8 steps (1 KB per pixel at cin = 512) are in flight per lane; the 3 x cin weights
+// sit in shared memory.  (The first version gave a whole warp to ONE pixel at a time — 15 shuffles and 2 loads per pixel —
+// and ran at 0.72 TB/s: 1.5 ms per 16 images, a third of the VQ-VAE round trip; profiles/r02_ncu_full_vqvae_summary.txt.)
+constexpr int C1_MAXJ = 8;      // cin <= 512 in one pass; larger cin loops
 __global__ void __launch_bounds__(256)
 conv1x1_out3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out,
                     size_t npix, int hw, int cin) {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ float w_s[];                 // [3][cin]
+    for (int i = threadIdx.x; i < 3 * cin; i += blockDim.x) w_s[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane & 7, pl = lane >> 3;
     const size_t warp_global = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t p0 = warp_global * 32; p0 < npix; p0 += nwarps * 32) {
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-        for (int pp = 0; pp < 32; ++pp) {
-            const size_t pix = p0 + pp;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            if (pix < npix) {
-                const __nv_bfloat16* xr = x + pix * cin;
-                for (int k = lane * 8; k < cin; k += 256) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(xr + k);
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const int nj = cin / 64;                       // 16-byte steps per lane (cin % 64 == 0)
+    const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
+    const float s0 = scale[0], s1 = scale[1], s2 = scale[2], t0 = shift[0], t1 = shift[1], t2 = shift[2];
+    for (size_t p0 = warp_global * 4; p0 < npix; p0 += nwarps * 4) {
+        const size_t pix = p0 + pl;
+        const bool ok = pix < npix;
+        const __nv_bfloat16* xr = x + (ok ? pix : p0) * cin + sub * 8;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int j0 = 0; j0 < nj; j0 += C1_MAXJ) {
+            uint4 u[C1_MAXJ];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float v0 = __low2float(h2[t]), v1 = __high2float(h2[t]);
-                        const int kk = k + 2 * t;
-                        a0 = fmaf(v0, w[kk], fmaf(v1, w[kk + 1], a0));
-                        a1 = fmaf(v0, w[cin + kk], fmaf(v1, w[cin + kk + 1], a1));
-                        a2 = fmaf(v0, w[2 * cin + kk], fmaf(v1, w[2 * cin + kk + 1], a2));
+            for (int j = 0; j < C1_MAXJ; ++j)
+                u[j] = (j0 + j < nj) ? *reinterpret_cast<const uint4*>(xr + (j0 + j) * 64) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < C1_MAXJ; ++j) {
+                if (j0 + j < nj) {
+                    const int k = (j0 + j) * 64 + sub * 8;
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+                    float v[8];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { v[2 * t] = __low2float(h2[t]); v[2 * t + 1] = __high2float(h2[t]); }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 wa = *reinterpret_cast<const float4*>(w_s + c * cin + k);
+                        const float4 wb = *reinterpret_cast<const float4*>(w_s + c * cin + k + 4);
+                        float acc = c == 0 ? a0 : (c == 1 ? a1 : a2);
+                        acc = fmaf(v[0], wa.x, acc); acc = fmaf(v[1], wa.y, acc); acc = fmaf(v[2], wa.z, acc);
+                        acc = fmaf(v[3], wa.w, acc); acc = fmaf(v[4], wb.x, acc); acc = fmaf(v[5], wb.y, acc);
+                        acc = fmaf(v[6], wb.z, acc); acc = fmaf(v[7], wb.w, acc);
+                        if (c == 0) a0 = acc; else if (c == 1) a1 = acc; else a2 = acc;
                     }
                 }
             }
-            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-            if (lane == pp) { r0 = a0; r1 = a1; r2 = a2; }
         }
-        const size_t pix = p0 + lane;
-        if (pix < npix) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {          // sum over the 8 lanes of the pixel
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (ok && sub == 0) {
             const size_t b = pix / hw, rem = pix % hw;
             float* o = out + b * 3 * hw + rem;
-            o[0] = (r0 + bias[0]) * scale[0] + shift[0];
-            o[hw] = (r1 + bias[1]) * scale[1] + shift[1];
-            o[2 * (size_t)hw] = (r2 + bias[2]) * scale[2] + shift[2];
+            o[0] = (a0 + b0) * s0 + t0;
+            o[hw] = (a1 + b1) * s1 + t1;
+            o[2 * (size_t)hw] = (a2 + b2) * s2 + t2;
         }
     }
 }
@@ -247,9 +272,10 @@ extern "C" int cv_im2col_k4s2_c3(const float* img, void* out, int B, int H, int 
 extern "C" int cv_conv1x1_out3(const void* x, const float* w, const float* bias, const float* scale, const float* shift,
                                float* out, int B, int H, int W, int cin, void* stream) {
     CV_REQUIRE(x && w && bias && scale && shift && out, "null pointer");
-    CV_REQUIRE(cin % 8 == 0 && B > 0 && H > 0 && W > 0, "cin must be a multiple of 8");
+    CV_REQUIRE(cin % 64 == 0 && cin <= 4096 && B > 0 && H > 0 && W > 0, "cin must be a multiple of 64 (<= 4096)");
     const size_t npix = (size_t)B * H * W;
-    conv1x1_out3_kernel<<<grid_for(npix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    conv1x1_out3_kernel<<<grid_for((npix + 3) / 4 * 32, 256), 256, (size_t)3 * cin * sizeof(float),
+                          static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), w, bias, scale, shift, out, npix, H * W, cin);
     CV_LAUNCH_CHECK();
     return 0;
