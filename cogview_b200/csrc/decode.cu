@@ -337,9 +337,15 @@ struct DecodeParams {
     float* partial;             // [b, heads, nsplit, HD + 2] when nsplit > 1
     int heads, nsplit, max_len;
     float scale_log2;
+    // GATHER (sparse_attention_inference, mpu/sparse_transformer.py:727-750, for sq = 1): the key set is the index list
+    // idx[batch][0 .. *n_dev) (pivots + trailing window, the new token's position cur_len among them) instead of 0..t
+    const int* idx;
+    int64_t idx_bs;
+    const int* n_dev;
 };
 
 // 8 lanes cooperate on one key (8 dims each); a warp covers 4 keys per iteration.
+template <bool GATHER>
 __global__ void __launch_bounds__(DA_WARPS * 32)
 attn_decode_kernel(const DecodeParams p) {
     __shared__ float s_m[DA_WARPS * 4], s_l[DA_WARPS * 4];
@@ -362,7 +368,8 @@ attn_decode_kernel(const DecodeParams p) {
         *reinterpret_cast<uint4*>(kbase + (size_t)t * 2 * h) = knew;
         *reinterpret_cast<uint4*>(kbase + (size_t)t * 2 * h + h) = vnew;
     }
-    const int total = t + 1;                                    // keys 0..t
+    const int total = GATHER ? *p.n_dev : t + 1;                // keys 0..t, or the gathered list
+    const int* my_idx = GATHER ? p.idx + (size_t)batch * p.idx_bs : nullptr;
     const int per = (total + p.nsplit - 1) / p.nsplit;
     const int j0 = split * per, j1 = min(total, j0 + per);
     float m = -INFINITY, l = 0.f, acc[8];
@@ -376,8 +383,9 @@ attn_decode_kernel(const DecodeParams p) {
         bool valid[DA_UNROLL];
 #pragma unroll
         for (int u = 0; u < DA_UNROLL; ++u) {
-            const int j = jb + u * DA_WARPS * 4 + grp;
-            valid[u] = j < j1;
+            const int jj = jb + u * DA_WARPS * 4 + grp;
+            valid[u] = jj < j1;
+            const int j = (GATHER && valid[u]) ? my_idx[jj] : jj;       // cache position of this key
             kr[u] = knew;
             vr[u] = vnew;
             if (valid[u] && j != t) {
@@ -647,8 +655,9 @@ extern "C" int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_
     p.partial = workspace;
     p.heads = heads; p.nsplit = nsplit; p.max_len = max_len;
     p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
+    p.idx = nullptr; p.idx_bs = 0; p.n_dev = nullptr;
     dim3 grid(heads, b, nsplit);
-    CV_CUDA(cvh::launch_pdl(attn_decode_kernel, grid, dim3(DA_WARPS * 32), 0, s, true, p));
+    CV_CUDA(cvh::launch_pdl(attn_decode_kernel<false>, grid, dim3(DA_WARPS * 32), 0, s, true, p));
     cvh::count_launches(1);
     if (nsplit > 1) {
         CV_CUDA(cvh::launch_pdl(attn_decode_combine_kernel, dim3(heads, b), dim3(HD), 0, s, true,
@@ -673,5 +682,128 @@ extern "C" int cv_attn_gather(const void* q, int64_t ldq, int64_t bsq, const voi
     p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
     attn_gather_kernel<<<dim3(heads, b, sq), DA_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
     CV_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Sparse inference on the device (is_sparse == 2, mpu/sparse_transformer.py:498-520, :591-600): the index plan of one
+// decode step for EVERY layer in one launch.  Per (layer, sequence): all text positions before the trailing window plus a
+// uniformly random subset of the image positions before it (num_pivot entries in total), then the window.  The reference
+// draws the subset with Python's random.sample per layer per token on the host (50 ms per token at 3000 positions);
+// here every candidate gets a counter-based random key and the smallest keys win — the same distribution (a uniformly
+// random k-subset, fresh per layer and token), a different random stream.  One 64-bit bitonic sort per CTA orders
+// "text first (key 0), then images by random key"; the first num_pivot entries are the pivots.
+// ------------------------------------------------------------------------------------------------
+constexpr int SP_THREADS = 1024;
+constexpr int SP_MAXPOS = 4096;
+
+__device__ __forceinline__ uint32_t sp_hash(uint64_t seed, uint32_t t, uint32_t layer, uint32_t b, uint32_t pos) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((((uint64_t)t << 32) | pos) + 0x632BE59BD9B4E019ull * (((uint64_t)layer << 16) | b));
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 33);          // 31 bits
+}
+
+__global__ void __launch_bounds__(SP_THREADS)
+sparse_plan_kernel(const uint8_t* __restrict__ is_txt, int64_t txt_bs, const int* __restrict__ cur_len_dev, int b,
+                   int window, double ratio, const unsigned long long* __restrict__ seed_dev, int* __restrict__ idx,
+                   int nmax, int* __restrict__ n_dev, int* __restrict__ err) {
+    __shared__ unsigned long long keys[SP_MAXPOS];
+    __shared__ int s_cnt[16];
+    const int layer = blockIdx.x, bb = blockIdx.y, tid = threadIdx.x;
+    const int t = *cur_len_dev, key_length = t + 1;
+    const int lb = max(0, key_length - window);
+    if (tid < 16) s_cnt[tid] = 0;
+    __syncthreads();
+    // text count of every sequence before the window (the reference sizes the pivot set by the maximum, :508-510)
+    for (int q = 0; q < b; ++q) {
+        int c = 0;
+        for (int pp = tid; pp < lb; pp += SP_THREADS) c += is_txt[(size_t)q * txt_bs + pp] ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[q], c);
+    }
+    __syncthreads();
+    int max_txt = 0;
+    for (int q = 0; q < b; ++q) max_txt = max(max_txt, s_cnt[q]);
+    const int num_pivot = max_txt + (int)((double)(lb - max_txt) * ratio);
+    const int n_win = key_length - lb;
+    if (num_pivot + n_win > nmax || lb > SP_MAXPOS) {
+        if (tid == 0 && err) atomicExch(err, 1);
+        return;
+    }
+    int n2 = 1;
+    while (n2 < lb) n2 <<= 1;
+    const unsigned long long seed = *seed_dev;
+    for (int pp = tid; pp < n2; pp += SP_THREADS) {
+        unsigned long long k = ~0ull;
+        if (pp < lb)
+            k = is_txt[(size_t)bb * txt_bs + pp] ? (unsigned long long)pp
+                                                : (((unsigned long long)(1u + sp_hash(seed, (uint32_t)t, layer, bb, pp))) << 32) | (unsigned)pp;
+        keys[pp] = k;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += SP_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], c = keys[ixj];
+                    const bool up = (i & k2) == 0;
+                    if ((a > c) == up) { keys[i] = c; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    int* out = idx + ((size_t)layer * b + bb) * nmax;
+    for (int i = tid; i < num_pivot; i += SP_THREADS) out[i] = (int)(keys[i] & 0xffffffffull);
+    for (int i = tid; i < n_win; i += SP_THREADS) out[num_pivot + i] = lb + i;
+    if (layer == 0 && bb == 0 && tid == 0) *n_dev = num_pivot + n_win;
+}
+
+extern "C" int cv_sparse_plan(const void* is_txt, int64_t txt_batch_stride, const int* cur_len_dev, int num_layers,
+                              int b, int window, int num_pivot, int max_sequence_length, const void* seed_dev, int* idx,
+                              int nmax, int* n_dev, int* err, void* stream) {
+    CV_REQUIRE(is_txt && cur_len_dev && seed_dev && idx && n_dev, "null pointer");
+    CV_REQUIRE(num_layers > 0 && b > 0 && b <= 16 && window > 0 && num_pivot >= 0 && max_sequence_length > 0 && nmax > 0,
+               "bad sizes (batch <= 16)");
+    sparse_plan_kernel<<<dim3(num_layers, b), SP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(is_txt), txt_batch_stride, cur_len_dev, b, window,
+        (double)num_pivot / (double)max_sequence_length, static_cast<const unsigned long long*>(seed_dev), idx, nmax, n_dev,
+        err);
+    CV_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cv_attn_decode_gather(const void* qkv, void* cache, int64_t cache_batch_stride, const int* cur_len_dev,
+                                     const int* idx, int64_t idx_batch_stride, const int* n_dev, void* out,
+                                     float* workspace, int b, int heads, int head_dim, int max_len, int nsplit,
+                                     void* stream) {
+    CV_REQUIRE(qkv && cache && out && cur_len_dev && idx && n_dev, "null pointer");
+    CV_REQUIRE(head_dim == HD, "head_dim must be 64");
+    CV_REQUIRE(b > 0 && heads > 0 && max_len > 0 && nsplit >= 1 && nsplit <= 64, "bad sizes");
+    CV_REQUIRE(nsplit == 1 || workspace != nullptr, "workspace required when nsplit > 1");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DecodeParams p;
+    p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+    p.cache = static_cast<__nv_bfloat16*>(cache);
+    p.cache_bs = cache_batch_stride;
+    p.cur_len_dev = cur_len_dev;
+    p.cur_len = -1;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.partial = workspace;
+    p.heads = heads; p.nsplit = nsplit; p.max_len = max_len;
+    p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
+    p.idx = idx; p.idx_bs = idx_batch_stride; p.n_dev = n_dev;
+    dim3 grid(heads, b, nsplit);
+    CV_CUDA(cvh::launch_pdl(attn_decode_kernel<true>, grid, dim3(DA_WARPS * 32), 0, s, true, p));
+    cvh::count_launches(1);
+    if (nsplit > 1) {
+        CV_CUDA(cvh::launch_pdl(attn_decode_combine_kernel, dim3(heads, b), dim3(HD), 0, s, true,
+                                static_cast<const float*>(workspace), static_cast<__nv_bfloat16*>(out), heads, nsplit));
+        cvh::count_launches(1);
+    }
     return 0;
 }

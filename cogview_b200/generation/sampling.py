@@ -10,6 +10,7 @@ Same call signatures and semantics; two host-side differences that do not change
     the vocabulary sizes alone (the role FakeTokenizer plays in data_utils/unified_tokenizer.py:208-212).
 """
 import math
+import os as _os
 
 import numpy as np
 import torch
@@ -216,10 +217,13 @@ def filling_sequence(model, seq, args, mems=None, invalid_slices=[], **kwargs):
             while counter + 1 + run < out_seq_length and tmpl[counter + 1 + run] == nxt:
                 run += 1
             first_pos = counter - offset if counter > offset else counter
-            if (run >= 2 and index == counter and tokens.shape[0] == -nxt and args.top_p == 0.0 and is_sparse == 0
+            device_pivots = is_sparse == 2 and _os.environ.get('COGVIEW_B200_SPARSE_PIVOTS', 'device') != 'host'
+            if (run >= 2 and index == counter and tokens.shape[0] == -nxt and args.top_p == 0.0
+                    and (is_sparse == 0 or device_pivots)
                     and not (counter <= offset < counter + run) and hasattr(model, 'generate_run')):
+                sparse = dict(n_img=n_img, tokens=tokens) if is_sparse == 2 else None
                 res = model.generate_run(tokens[:, counter:], first_pos, mems, run, args.temperature, args.top_k,
-                                         invalid_slices)
+                                         invalid_slices, sparse=sparse)
                 if res is not None:
                     new_tokens, logp, mems = res
                     if -nxt > 1:

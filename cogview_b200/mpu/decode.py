@@ -59,6 +59,12 @@ class DecodeRunner:
         self.score_acc = torch.zeros(self.b, dtype=torch.float32, device=dev)
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.done = torch.zeros(1, dtype=torch.int32, device=dev)
+        # sparse inference on the device (is_sparse == 2): text flags of every position, the per-layer key index lists of
+        # the current step (cv_sparse_plan) and their common length
+        self.sparse = None               # dict(n_img) while a sparse run is being captured / replayed
+        self.window = tr.query_window * tr.key_window_times
+        self.nmax = tr.num_pivot + self.window
+        self.is_txt = None
 
     # -- parameters --------------------------------------------------------------------------------------------
     def _signature(self):
@@ -90,8 +96,18 @@ class DecodeRunner:
             self._gather_params()
 
     # -- one step ----------------------------------------------------------------------------------------------
+    def _ensure_sparse_buffers(self):
+        if self.is_txt is None:
+            dev = self.ids.device
+            L = len(self.model.transformer.layers)
+            self.is_txt = torch.zeros((self.b, self.caches.maxlen + 1), dtype=torch.uint8, device=dev)
+            self.key_idx = torch.zeros((L, self.b, self.nmax), dtype=torch.int32, device=dev)
+            self.n_keys = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.plan_err = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.len64 = torch.zeros((1, 1), dtype=torch.int64, device=dev)
+
     def _run(self):
-        if self.persistent:
+        if self.persistent and self.sparse is None:
             ops.decode_step(self.layer_table, len(self.params), self.heads, self.eps, self.fl[2], self.wte, self.wpe,
                             self.fl[0], self.fl[1], self.ids, self.pos, self.cur_len, self.caches.buf,
                             self.step_logits, self.workspace)
@@ -102,6 +118,14 @@ class DecodeRunner:
         b, h, heads = self.b, self.h, self.heads
         L = len(self.params)
         scal = ops.new_scalars(2 * L + 1, self.ids.device)
+        sparse = self.sparse
+        if sparse is not None:
+            # the fed token's text flag, then the key lists of all layers for this step (pivots are fresh per layer and
+            # per token as in mpu/sparse_transformer.py:591-600, drawn on the device)
+            tr = self.model.transformer
+            self.is_txt.scatter_(1, self.len64.expand(b, 1), (self.ids >= sparse['n_img']).to(torch.uint8))
+            ops.sparse_plan(self.is_txt, self.cur_len, L, self.window, tr.num_pivot, tr.max_sequence_length, self.seed_dev,
+                            self.key_idx, self.n_keys, self.plan_err)
         x = ops.embed_fwd(self.ids, self.pos, self.wte, self.wpe, scal[2 * L:2 * L + 1])
         prev_gemm = prev_am = prev_post = None
         for i, P in enumerate(self.params):
@@ -113,7 +137,11 @@ class DecodeRunner:
             if y is not None:
                 x = y
             qkv = ops.linear_small_m(xn, wqkv, bqkv)
-            ctx = ops.attn_decode(qkv, self.caches.buf[i], heads, cur_len_dev=self.cur_len, nsplit=self.nsplit)
+            if sparse is not None:
+                ctx = ops.attn_decode_gather(qkv, self.caches.buf[i], heads, self.cur_len, self.key_idx[i], self.n_keys,
+                                             nsplit=self.nsplit)
+            else:
+                ctx = ops.attn_decode(qkv, self.caches.buf[i], heads, cur_len_dev=self.cur_len, nsplit=self.nsplit)
             attn_out = ops.linear_small_m(ctx, wd, bd, absmax=s[0:1])
             # y = x + LN3(attn_out);  xn2 = LN2(y)
             x, xn2 = ops.ln_pair_small_m(x, attn_out, s[0:1], (g3, b3), (g2, b2), self.eps)
@@ -164,8 +192,10 @@ class DecodeRunner:
         the sampled token to the next step, all through device-side state.  With the fused kernel the tail is ONE
         launch (cv_sample_topk, own counter-based generator); COGVIEW_B200_FUSED_SAMPLING=0 keeps the reference's
         torch operations (torch.multinomial's generator) instead."""
-        temperature, top_k, inv = key
+        temperature, top_k, inv = key[:3]
         logits = self._run()
+        if self.sparse is not None:
+            self.len64.add_(1)
         vocab = logits.shape[1]
         valid = ops.valid_ranges(inv, vocab)
         if os.environ.get('COGVIEW_B200_FUSED_SAMPLING', '1') != '0' and 1 <= len(valid) <= 4:
@@ -196,15 +226,27 @@ class DecodeRunner:
         self.stepc.zero_()
         self.score_acc.zero_()
 
-    def sample_run(self, ids, pos, t, n_steps, temperature, top_k, invalid_slices):
+    def sample_run(self, ids, pos, t, n_steps, temperature, top_k, invalid_slices, sparse=None):
         """n_steps tokens starting from `ids` ([b, 1], at positions `pos`, t tokens cached).  One graph replay per
-        token.  Returns (tokens [b, n_steps] int64, summed log-probabilities [b] fp32)."""
+        token.  Returns (tokens [b, n_steps] int64, summed log-probabilities [b] fp32).
+        sparse: None, or dict(n_img=..., tokens=[b, t + 1] every token so far) for is_sparse == 2."""
         self._check_params()
         self.last_t = t + n_steps
         vocab = self.model.word_embeddings.weight.shape[0]
-        key = (float(temperature), int(top_k), tuple(sl.indices(vocab)[:2] for sl in invalid_slices))
+        key = (float(temperature), int(top_k), tuple(sl.indices(vocab)[:2] for sl in invalid_slices),
+               None if sparse is None else int(sparse['n_img']))
         assert n_steps <= self.out_buf.shape[1]
         self._reset_run(ids, pos, t)
+        self.sparse = None
+        if sparse is not None:
+            self._ensure_sparse_buffers()
+            self.sparse = dict(n_img=int(sparse['n_img']))
+            hist = sparse['tokens']
+            assert hist.shape == (self.b, t + 1)
+            self.is_txt.zero_()
+            self.is_txt[:, :t + 1] = (hist >= self.sparse['n_img']).to(torch.uint8)
+            self.len64.fill_(t)
+            self.plan_err.zero_()
         # the draw generator of the fused tail: a fresh seed per run from torch's (seedable) host generator
         self.seed_dev.copy_(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64), non_blocking=True)
         graph = self.sample_graphs.get(key)
@@ -232,4 +274,8 @@ class DecodeRunner:
             else:
                 graph.replay()
         self.replays += n_steps
+        if self.sparse is not None:
+            self.sparse = None
+            if int(self.plan_err.item()) != 0:
+                raise RuntimeError('sparse decode: the key list did not fit num_pivot + window entries')
         return self.out_buf[:, :n_steps].clone(), self.score_acc.clone()

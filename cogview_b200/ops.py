@@ -320,6 +320,38 @@ def attn_decode(qkv, cache, heads, *, cur_len=None, cur_len_dev=None, nsplit=1, 
     return out
 
 
+def sparse_plan(is_txt, cur_len_dev, num_layers, window, num_pivot, max_sequence_length, seed_dev, idx, n_dev, err):
+    """Index plan of one sparse decode step for every layer (cv_sparse_plan).  is_txt: uint8 [b, max_len]; idx: int32
+    [num_layers, b, nmax] (written); n_dev, err: int32 [1]; seed_dev: int64 [1]."""
+    require_cuda(is_txt, cur_len_dev, seed_dev, idx, n_dev, err)
+    assert is_txt.dtype == torch.uint8 and is_txt.stride(1) == 1 and idx.dtype == torch.int32 and idx.is_contiguous()
+    assert cur_len_dev.dtype == torch.int32 and n_dev.dtype == torch.int32 and seed_dev.dtype == torch.int64
+    L, b, nmax = idx.shape
+    assert L == num_layers and is_txt.shape[0] == b
+    check(lib().cv_sparse_plan(ptr(is_txt), is_txt.stride(0), ptr(cur_len_dev), int(num_layers), b, int(window),
+                               int(num_pivot), int(max_sequence_length), ptr(seed_dev), ptr(idx), nmax, ptr(n_dev),
+                               ptr(err), stream_ptr()), "cv_sparse_plan")
+
+
+def attn_decode_gather(qkv, cache, heads, cur_len_dev, idx, n_dev, *, nsplit=1, out=None, workspace=None):
+    """attn_decode over the key list idx [b, nmax] int32 (first *n_dev entries; it contains the new token's position)."""
+    require_cuda(qkv, cache, idx, n_dev, cur_len_dev)
+    b, h3 = qkv.shape
+    h = h3 // 3
+    assert qkv.is_contiguous() and cache.stride(2) == 1 and cache.stride(1) == 2 * h and cache.shape[2] == 2 * h
+    assert idx.dtype == torch.int32 and idx.shape[0] == b and idx.stride(1) == 1
+    if out is None:
+        out = torch.empty((b, h), dtype=torch.bfloat16, device=qkv.device)
+    if nsplit > 1 and workspace is None:
+        workspace = torch.empty(lib().cv_attn_decode_workspace_bytes(b, heads, nsplit) // 4, dtype=torch.float32,
+                                device=qkv.device)
+    rc = lib().cv_attn_decode_gather(ptr(qkv), ptr(cache), cache.stride(0), ptr(cur_len_dev), ptr(idx), idx.stride(0),
+                                     ptr(n_dev), ptr(out), ptr(workspace), b, heads, 64, cache.shape[1], nsplit,
+                                     stream_ptr())
+    check(rc, "cv_attn_decode_gather")
+    return out
+
+
 def ln_pair_small_m(res_in, gemm_out, absmax_gemm, post, pre, eps, *, want_res_out=True):
     """y = res_in + LN_post(gemm_out) (gemm_out may be None), xn = LN_pre(y).  post/pre: (gamma, beta) bf16.
     Returns (y fp32 or None, xn bf16)."""

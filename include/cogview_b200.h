@@ -192,6 +192,22 @@ int64_t cv_attn_decode_workspace_bytes(int b, int heads, int nsplit);
 int cv_attn_decode(const void* qkv, void* cache, int64_t cache_batch_stride, const int* cur_len_dev, int cur_len,
                    void* out, float* workspace, int b, int heads, int head_dim, int max_len, int nsplit,
                    void* stream);
+/* Sparse inference (is_sparse == 2, mpu/sparse_transformer.py:498-520, :591-600, :727-750) without the host:
+ *   cv_sparse_plan: the key index list of one decode step for EVERY layer: idx [num_layers, b, nmax] int32, *n_dev = its
+ *     length.  Per (layer, sequence): every text position before the trailing window (is_txt [b, max_len] uint8 marks
+ *     them), a uniformly random subset of the image positions before it — num_pivot_now = max_text +
+ *     int((left_boundary - max_text) * num_pivot / max_sequence_length) entries in total, as :508-510 — then the window
+ *     [left_boundary, *cur_len_dev].  The subset is drawn with counter-based random keys (seed *seed_dev, the step, the
+ *     layer, the sequence, the position): the distribution of random.sample, not its stream.  *err is set to 1 if the
+ *     list does not fit nmax.  batch <= 16, positions <= 4096.
+ *   cv_attn_decode_gather: cv_attn_decode over that key list (idx + batch * idx_batch_stride, *n_dev entries; the new
+ *     token's position *cur_len_dev must be in the list — it is the last window entry) with the same fused append. */
+int cv_sparse_plan(const void* is_txt, int64_t txt_batch_stride, const int* cur_len_dev, int num_layers, int b, int window,
+                   int num_pivot, int max_sequence_length, const void* seed_dev, int* idx, int nmax, int* n_dev, int* err,
+                   void* stream);
+int cv_attn_decode_gather(const void* qkv, void* cache, int64_t cache_batch_stride, const int* cur_len_dev, const int* idx,
+                          int64_t idx_batch_stride, const int* n_dev, void* out, float* workspace, int b, int heads,
+                          int head_dim, int max_len, int nsplit, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole decode step as ONE persistent kernel (1 <= batch <= 8): what GPT2Model.forward (model/gpt2_modeling.py:106-123)
