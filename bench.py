@@ -821,7 +821,8 @@ def main():
                                            gemm_frac_of_burst_peak=t["roofline"]["frac"], loss=t["loss"],
                                            exposed_comm_ms=t.get("exposed_comm_ms"))
         line["train"] = t
-    if rank == 0 and args.skip_cpu_baseline:        # development runs only: the contract line carries cpu_baseline
+    if rank == 0 and (args.skip_cpu_baseline or world > 1):
+        # the CPU baseline is reported at N = 1 only (--skip-cpu-baseline: development runs)
         line["cpu_baseline"] = None
         print(json.dumps(line))
     elif rank == 0:

@@ -77,14 +77,23 @@ def load():
         sys.path.insert(0, REFERENCE_ROOT)
     import torch.distributed as dist
     if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group("gloo", rank=0, world_size=1)
+        # a private single-rank gloo group on a free local port: independent of any torchrun rendezvous variables in the
+        # environment (bench.py --impl reference is launched under torchrun for N > 1, rank 0 alone does the work)
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
     import mpu  # noqa: the reference's package
     import mpu.sparse_transformer as st
-    if not torch.cuda.is_available():
-        st.get_cuda_rng_tracker = lambda: _NoRng()
     mpu.initialize_model_parallel(1)
+    if torch.cuda.is_available():
+        # a CUDA box (the GPU host timing the CPU arm): do what the reference's own entry points do before building the
+        # model (pretrain_gpt2.py set_random_seed -> mpu.model_parallel_cuda_manual_seed), so that the RNG tracker that
+        # standard_attention forks (mpu/sparse_transformer.py:667-669) knows its 'model-parallel-rng' state
+        mpu.model_parallel_cuda_manual_seed(1234)
+    else:
+        st.get_cuda_rng_tracker = lambda: _NoRng()
     from model import gpt2_modeling
     import vqvae.api as vq_api
     import vqvae.vqvae_zc as vq_zc
