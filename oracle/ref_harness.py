@@ -77,13 +77,12 @@ def load():
         sys.path.insert(0, REFERENCE_ROOT)
     import torch.distributed as dist
     if not dist.is_initialized():
-        # a private single-rank gloo group on a free local port: independent of any torchrun rendezvous variables in the
-        # environment (bench.py --impl reference is launched under torchrun for N > 1, rank 0 alone does the work)
-        import socket
-        with socket.socket() as sk:
-            sk.bind(("127.0.0.1", 0))
-            port = sk.getsockname()[1]
-        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+        # a private single-rank gloo group through a file store: independent of any torchrun rendezvous in the environment
+        # (bench.py --impl reference is launched under torchrun for N > 1 and rank 0 alone does the work; with
+        # TORCHELASTIC_USE_AGENT_STORE set, env:// and tcp:// would try to join the agent's store as a client and block)
+        import tempfile
+        store_file = os.path.join(tempfile.mkdtemp(prefix="cogview_ref_pg_"), "store")
+        dist.init_process_group("gloo", init_method="file://" + store_file, rank=0, world_size=1)
     import mpu  # noqa: the reference's package
     import mpu.sparse_transformer as st
     mpu.initialize_model_parallel(1)

@@ -174,3 +174,24 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == ("reference" if ref_here else "port")
     assert d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reference_arm_under_torchrun_does_not_wait_for_a_rendezvous():
+    """The driver launches `bench.py --impl reference --gpus N` under torchrun for N > 1: rank 0 alone does the work and
+    prints the line, the other ranks exit 0.  The reference's mpu needs a process group — it must be a private one (a
+    file store): with TORCHELASTIC_USE_AGENT_STORE in the environment an env:// or tcp:// group would try to join the
+    agent's store as a client and block until its timeout."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(root, "bench.py"), "--impl",
+                        "reference", "--gpus", "2", "--model", "tiny", "--steps", "1", "--warmup", "0", "--gen-tokens", "16"],
+                       capture_output=True, text=True, timeout=240, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
