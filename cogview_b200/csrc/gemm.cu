@@ -49,6 +49,8 @@ struct GemmParams {
     void* c;                    // output [M, N] (bf16 or fp32), leading dimension ldc
     __nv_bfloat16* c2;          // optional pre-activation output (bf16, same ldc)
     int64_t ldc;
+    int vec32;                  // C and C2 rows start 32-byte aligned: 256-bit stores
+    int dbg;                    // timing experiments (COGVIEW_B200_GEMM_DBG): 1 = no global stores, 2 = no TMEM loads
 };
 
 // Tail-wave splitting: with T tiles on G persistent CTAs the last T % G tiles would occupy a whole wave while most
@@ -70,6 +72,40 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile) {
         t.width = BN / 2;
     }
     return t;
+}
+
+// 32-byte (whole-sector) global store: the epilogue threads write rows that are kilobytes apart, so a 16-byte store is
+// half a sector per lane — with 16-byte stores the C writes cost 14 % of the QKV GEMM (128 us; 110 us with the stores
+// compiled out, tools/gemm_dbg_bench.py)
+__device__ __forceinline__ uint32_t r_as_u32(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                             uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+                 "r"(f), "r"(g), "r"(h) : "memory");
+}
+// 16 consecutive bf16 outputs of one row: one 32-byte store when the row is 32-byte aligned and the group is inside
+// [0, N), else two 16-byte groups / scalar tail
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v, int n, int N, bool vec32, bool n_vec_ok) {
+    if (vec32 && n + 16 <= N) {
+        st_global_v8(dst, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]),
+                     pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        return;
+    }
+#pragma unroll
+    for (int hgrp = 0; hgrp < 2; ++hgrp) {
+        const int nn = n + hgrp * 8;
+        const float* vv = v + hgrp * 8;
+        if (n_vec_ok && nn + 8 <= N) {
+            uint4 o;
+            o.x = pack_bf16x2(vv[0], vv[1]); o.y = pack_bf16x2(vv[2], vv[3]);
+            o.z = pack_bf16x2(vv[4], vv[5]); o.w = pack_bf16x2(vv[6], vv[7]);
+            *reinterpret_cast<uint4*>(dst + hgrp * 8) = o;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (nn + t < N) dst[hgrp * 8 + t] = __float2bfloat16_rn(vv[t]);
+        }
+    }
 }
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
@@ -205,7 +241,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int c = 0; c < nchunk; ++c) {
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * EPI_COLS;
                 uint32_t r[EPI_COLS];
-                {
+                if (p.dbg & 2) {
+#pragma unroll
+                    for (int j = 0; j < EPI_COLS; ++j) r[j] = j + c;
+                } else {
                     uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
                     tmem_ld_x32(taddr, r0);
                     if (EPI_COLS == 64) {
@@ -245,19 +284,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (p.has_c2 && row_ok) {   // pre-activation copy (bf16)
                     __nv_bfloat16* dst = p.c2 + (size_t)grow * p.ldc + ncol0;
 #pragma unroll
-                    for (int g = 0; g < EPI_COLS / 8; ++g) {
-                        const int n = ncol0 + g * 8;
-                        if (n_vec_ok && n + 8 <= p.N) {
-                            uint4 o;
-                            o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-                            o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-                            *reinterpret_cast<uint4*>(dst + g * 8) = o;
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 8; ++t)
-                                if (n + t < p.N) dst[g * 8 + t] = __float2bfloat16_rn(v[8 * g + t]);
-                        }
-                    }
+                    for (int g = 0; g < EPI_COLS / 16; ++g)
+                        store_bf16x16(dst + g * 16, v + g * 16, ncol0 + g * 16, p.N, p.vec32 != 0, n_vec_ok);
                 }
                 if (p.act == 1) {
 #pragma unroll
@@ -292,13 +320,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         dropout4(p.drop, idx4, v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
                     }
                 }
-                if (row_ok) {
+                if (row_ok && !(p.dbg & 1)) {
                     if (OUT_F32) {
                         float* dst = static_cast<float*>(p.c) + (size_t)grow * p.ldc + ncol0;
 #pragma unroll
                         for (int g = 0; g < EPI_COLS / 4; ++g) {
                             const int n = ncol0 + g * 4;
-                            if ((p.N % 4) == 0 && n + 4 <= p.N) {
+                            if (p.vec32 && (g & 1) == 0 && n + 8 <= p.N) {
+                                st_global_v8(dst + g * 4, r_as_u32(v[4 * g]), r_as_u32(v[4 * g + 1]), r_as_u32(v[4 * g + 2]),
+                                             r_as_u32(v[4 * g + 3]), r_as_u32(v[4 * g + 4]), r_as_u32(v[4 * g + 5]),
+                                             r_as_u32(v[4 * g + 6]), r_as_u32(v[4 * g + 7]));
+                            } else if (p.vec32 && (g & 1) == 1 && n + 4 <= p.N) {
+                                // written with the previous group (n - 4 + 8 <= N)
+                            } else if ((p.N % 4) == 0 && n + 4 <= p.N) {
                                 *reinterpret_cast<float4*>(dst + g * 4) =
                                     make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
                             } else {
@@ -315,19 +349,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     } else {
                         __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.c) + (size_t)grow * p.ldc + ncol0;
 #pragma unroll
-                        for (int g = 0; g < EPI_COLS / 8; ++g) {
-                            const int n = ncol0 + g * 8;
-                            if (n_vec_ok && n + 8 <= p.N) {
-                                uint4 o;
-                                o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-                                o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-                                *reinterpret_cast<uint4*>(dst + g * 8) = o;
-                            } else {
-#pragma unroll
-                                for (int t = 0; t < 8; ++t)
-                                    if (n + t < p.N) dst[g * 8 + t] = __float2bfloat16_rn(v[8 * g + t]);
-                            }
-                        }
+                        for (int g = 0; g < EPI_COLS / 16; ++g)
+                            store_bf16x16(dst + g * 16, v + g * 16, ncol0 + g * 16, p.N, p.vec32 != 0, n_vec_ok);
                         if (p.absmax != nullptr) {
 #pragma unroll
                             for (int j = 0; j < EPI_COLS; ++j)
@@ -450,6 +473,13 @@ static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, 
     p.c = Cout;
     p.c2 = static_cast<__nv_bfloat16*>(C2);
     p.ldc = ldc;
+    {
+        static const int dbg = [] { const char* e = getenv("COGVIEW_B200_GEMM_DBG"); return e ? atoi(e) : 0; }();
+        p.dbg = dbg;
+        const size_t esz = c_is_f32 ? 4 : 2;
+        p.vec32 = !(dbg & 4) && (reinterpret_cast<uintptr_t>(Cout) % 32 == 0) && ((ldc * esz) % 32 == 0) &&
+                  (C2 == nullptr || (reinterpret_cast<uintptr_t>(C2) % 32 == 0 && (ldc * 2) % 32 == 0));
+    }
 
     alignas(64) CUtensorMap tmA, tmB;
     int rc;
