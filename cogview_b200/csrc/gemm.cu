@@ -32,7 +32,8 @@ struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int CSTAGE_BYTES = 4 * 2 * 4096;   // C staging: 4 epilogue warps x 2 buffers x [32 rows x 128 B]
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -50,6 +51,7 @@ struct GemmParams {
     __nv_bfloat16* c2;          // optional pre-activation output (bf16, same ldc)
     int64_t ldc;
     int vec32;                  // C and C2 rows start 32-byte aligned: 256-bit stores
+    int tma_store;              // C (and C2) go through shared memory + cp.async.bulk.tensor stores (whole 128-byte lines)
     int dbg;                    // timing experiments (COGVIEW_B200_GEMM_DBG): 1 = no global stores, 2 = no TMEM loads
 };
 
@@ -110,11 +112,13 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint8_t* smem_c = smem + C::STAGES * C::STAGE_BYTES;     // 1024-byte aligned (stage sizes are multiples of 1024)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + C::CSTAGE_BYTES);
     uint64_t* full_bar = bars;                       // [STAGES]
     uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
     uint64_t* tmem_full = bars + 2 * C::STAGES;      // [2]
@@ -225,6 +229,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int row = q * 32 + lane;          // row within the tile
         constexpr int EPI_COLS = OUT_F32 ? 32 : 64;
         const bool n_vec_ok = (p.N % 8) == 0;   // whole 16-byte groups are either inside or outside [0, N)
+        // TMA-store path: the lane's 128-byte row of a chunk goes to this warp's 128B-swizzled [32 x 128 B] staging buffer
+        // (double-buffered), lane 0 issues one cp.async.bulk.tensor store per chunk: whole 128-byte lines leave the SM
+        // asynchronously instead of 32 scattered sector writes per store instruction; rows / columns outside C are
+        // clipped by the tensor map.
+        uint8_t* sC = smem_c + q * 8192;
+        int cc = 0;
+        auto put_row = [&](const CUtensorMap* tm, const float* vals, int col0, int row0) {
+            uint8_t* buf = sC + (cc & 1) * 4096;
+            if (cc >= 2) {
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+            }
+            uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint4 o;
+                if (OUT_F32) {
+                    o.x = __float_as_uint(vals[4 * j]); o.y = __float_as_uint(vals[4 * j + 1]);
+                    o.z = __float_as_uint(vals[4 * j + 2]); o.w = __float_as_uint(vals[4 * j + 3]);
+                } else {
+                    o.x = pack_bf16x2(vals[8 * j + 0], vals[8 * j + 1]); o.y = pack_bf16x2(vals[8 * j + 2], vals[8 * j + 3]);
+                    o.z = pack_bf16x2(vals[8 * j + 4], vals[8 * j + 5]); o.w = pack_bf16x2(vals[8 * j + 6], vals[8 * j + 7]);
+                }
+                *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(tm, buf, col0, row0);
+                tma_store_commit();
+            }
+            ++cc;
+        };
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = tile_coord<BN>(p, tile);
@@ -281,7 +318,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                 }
-                if (p.has_c2 && row_ok) {   // pre-activation copy (bf16)
+                if (p.has_c2 && p.tma_store) {
+                    put_row(&tmC2, v, ncol0, m0 + q * 32);
+                } else if (p.has_c2 && row_ok) {   // pre-activation copy (bf16)
                     __nv_bfloat16* dst = p.c2 + (size_t)grow * p.ldc + ncol0;
 #pragma unroll
                     for (int g = 0; g < EPI_COLS / 16; ++g)
@@ -320,7 +359,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         dropout4(p.drop, idx4, v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
                     }
                 }
-                if (row_ok && !(p.dbg & 1)) {
+                if (p.tma_store && !(p.dbg & 1)) {
+                    put_row(&tmC, v, ncol0, m0 + q * 32);
+                    if (p.absmax != nullptr && row_ok) {
+#pragma unroll
+                        for (int j = 0; j < EPI_COLS; ++j)
+                            if (ncol0 + j < p.N) tmax = fmaxf(tmax, fabsf(OUT_F32 ? v[j] : bf16_round(v[j])));
+                    }
+                } else if (row_ok && !(p.dbg & 1)) {
                     if (OUT_F32) {
                         float* dst = static_cast<float*>(p.c) + (size_t)grow * p.ldc + ncol0;
 #pragma unroll
@@ -364,6 +410,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (lane == 0 && tmax > 0.f) atomic_max_nonneg(p.absmax, tmax);
             }
         }
+        if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // the staging buffers must outlive their readers
     }
 
     tc_fence_before();
@@ -375,7 +422,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+           const GemmParams& p, cudaStream_t stream) {
     auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -385,7 +433,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
     }
     int tiles = p.num_tiles;
     int grid = tiles < cvh::gemm_sms() ? tiles : cvh::gemm_sms();
-    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cvh::fail_cuda("cv_gemm_bf16", e);
     cvh::count_launches(1);
@@ -393,17 +441,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
 }
 
 template <int BN>
-int dispatch(int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-             cudaStream_t s) {
+int dispatch(int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+             const CUtensorMap& tmC2, const GemmParams& p, cudaStream_t s) {
     if (out_f32) {
-        if (!a_mn && !b_mn) return launch<BN, false, false, true>(tmA, tmB, p, s);
-        if (!a_mn && b_mn) return launch<BN, false, true, true>(tmA, tmB, p, s);
-        if (a_mn && b_mn) return launch<BN, true, true, true>(tmA, tmB, p, s);
+        if (!a_mn && !b_mn) return launch<BN, false, false, true>(tmA, tmB, tmC, tmC2, p, s);
+        if (!a_mn && b_mn) return launch<BN, false, true, true>(tmA, tmB, tmC, tmC2, p, s);
+        if (a_mn && b_mn) return launch<BN, true, true, true>(tmA, tmB, tmC, tmC2, p, s);
         return cvh::fail_arg("cv_gemm_bf16", "A MN-major with B K-major is not instantiated");
     }
-    if (!a_mn && !b_mn) return launch<BN, false, false, false>(tmA, tmB, p, s);
-    if (!a_mn && b_mn) return launch<BN, false, true, false>(tmA, tmB, p, s);
-    if (a_mn && b_mn) return launch<BN, true, true, false>(tmA, tmB, p, s);
+    if (!a_mn && !b_mn) return launch<BN, false, false, false>(tmA, tmB, tmC, tmC2, p, s);
+    if (!a_mn && b_mn) return launch<BN, false, true, false>(tmA, tmB, tmC, tmC2, p, s);
+    if (a_mn && b_mn) return launch<BN, true, true, false>(tmA, tmB, tmC, tmC2, p, s);
     return cvh::fail_arg("cv_gemm_bf16", "A MN-major with B K-major is not instantiated");
 }
 
@@ -490,8 +538,23 @@ static int gemm_impl(const void* A, int a_mn_major, int64_t lda, const void* B, 
     rc = b_mn_major ? cvh::encode_tmap_2d_bf16(&tmB, B, K, N, ldb, BK, 64)
                     : cvh::encode_tmap_2d_bf16(&tmB, B, N, K, ldb, 128, BK);   // 128-row boxes: BN / 128 per stage
     if (rc) return rc;
-    if (BN == 256) return dispatch<256>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, p, s);
-    return dispatch<128>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, p, s);
+    // C (and the pre-activation copy) as [32-row x 128-byte] boxes for the epilogue's TMA stores
+    alignas(64) CUtensorMap tmC, tmC2;
+    p.tma_store = !(p.dbg & 8);
+    if (p.tma_store) {
+        rc = c_is_f32 ? cvh::encode_tmap_2d_f32(&tmC, Cout, M, N, ldc, 32, 32) : cvh::encode_tmap_2d_bf16(&tmC, Cout, M, N, ldc, 32, 64);
+        if (rc) return rc;
+        tmC2 = tmC;
+        if (p.has_c2) {
+            rc = cvh::encode_tmap_2d_bf16(&tmC2, C2, M, N, ldc, 32, 64);
+            if (rc) return rc;
+        }
+    } else {
+        tmC = tmA;
+        tmC2 = tmA;
+    }
+    if (BN == 256) return dispatch<256>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, tmC, tmC2, p, s);
+    return dispatch<128>(a_mn_major, b_mn_major, c_is_f32, tmA, tmB, tmC, tmC2, p, s);
 }
 
 extern "C" int cv_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
