@@ -229,6 +229,9 @@ def filling_sequence(model, seq, args, mems=None, invalid_slices=[], **kwargs):
                     if -nxt > 1:
                         score = (score if torch.is_tensor(score) else torch.tensor(score, device=device)) + logp
                     tokens = torch.cat((tokens, new_tokens), dim=1)
+                    if is_sparse == 2:
+                        img_indices_bool = tokens < n_img
+                        txt_indices_bool = ~img_indices_bool
                     counter += run
                     index = counter
                     continue

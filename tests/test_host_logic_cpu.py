@@ -195,3 +195,47 @@ def test_bench_reference_arm_under_torchrun_does_not_wait_for_a_rendezvous():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
+def test_filling_sequence_sparse_run_keeps_index_masks_current():
+    """filling_sequence with is_sparse == 2: a stretch of generate slots goes through model.generate_run(sparse=...) with the
+    full token history; the text / image index masks handed to the next host-loop call must cover the tokens the run
+    appended (mpu/sparse_transformer.py:498-520 indexes them by position)."""
+    from cogview_b200.generation import sampling
+
+    class A:
+        temperature, top_k, top_p, is_sparse = 1.0, 0, 0.0, 2
+        img_tokenizer_num_tokens = 8192
+    tok = sampling.get_tokenizer(A)
+    V = tok.num_tokens
+    calls = {"run": [], "fwd": []}
+
+    class StandIn:
+        def __call__(self, tokens, position_ids, attention_mask, txt, img, is_sparse, *mems):
+            assert is_sparse == 2 and txt is not None and img is not None
+            t_prev = mems[0].shape[1] if mems else 0
+            assert txt.shape == img.shape and txt.shape[1] == t_prev + tokens.shape[1]      # masks cover every position
+            calls["fwd"].append(tokens.shape)
+            b, sq = tokens.shape
+            g = torch.Generator().manual_seed(t_prev)
+            logits = torch.randn((b, sq, V), generator=g)
+            mem = torch.zeros((b, t_prev + sq, 1))
+            return (logits, mem)
+
+        def generate_run(self, last_tokens, first_pos, mems, n_steps, temperature, top_k, invalid_slices, sparse=None):
+            assert sparse is not None and sparse["n_img"] == 8192
+            assert sparse["tokens"].shape[1] == mems[0].shape[1] + 1                        # history incl. the fed token
+            calls["run"].append(n_steps)
+            b = last_tokens.shape[0]
+            new = torch.arange(n_steps).unsqueeze(0).expand(b, -1) % 8192
+            mem = torch.zeros((b, mems[0].shape[1] + n_steps, 1))
+            return new, torch.zeros(b), [mem]
+
+    text = list(range(8192, 8192 + 6))
+    seq = [tok['[ROI1]']] + text + [tok['[BASE]'], tok['[BOI1]']] + [-2] * 7 + [tok['[EOI1]']] + [-1]
+    out = sampling.filling_sequence(StandIn(), torch.tensor(seq, dtype=torch.long), A)
+    assert out.shape[1] == len(seq)
+    assert calls["run"] == [6]                 # the first of the seven -2 slots expands the beams on the host
+    # the context call, then (after the device run and the provided [EOI1]) one host-loop call fed with the two newest
+    # tokens — its masks were checked above against the memory length that includes the run's six tokens
+    assert len(calls["fwd"]) == 2 and calls["fwd"][-1][1] == 2
