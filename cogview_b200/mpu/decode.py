@@ -225,6 +225,12 @@ class DecodeRunner:
         self.cur_len.fill_(t)
         self.stepc.zero_()
         self.score_acc.zero_()
+        if self.sparse is not None:      # text flags of the history, flag cursor (the warm-up steps before a capture moved them)
+            flags = self.sparse['flags']
+            self.is_txt.zero_()
+            self.is_txt[:, :flags.shape[1]] = flags
+            self.len64.fill_(t)
+            self.plan_err.zero_()
 
     def sample_run(self, ids, pos, t, n_steps, temperature, top_k, invalid_slices, sparse=None):
         """n_steps tokens starting from `ids` ([b, 1], at positions `pos`, t tokens cached).  One graph replay per
@@ -236,17 +242,13 @@ class DecodeRunner:
         key = (float(temperature), int(top_k), tuple(sl.indices(vocab)[:2] for sl in invalid_slices),
                None if sparse is None else int(sparse['n_img']))
         assert n_steps <= self.out_buf.shape[1]
-        self._reset_run(ids, pos, t)
         self.sparse = None
         if sparse is not None:
             self._ensure_sparse_buffers()
-            self.sparse = dict(n_img=int(sparse['n_img']))
             hist = sparse['tokens']
             assert hist.shape == (self.b, t + 1)
-            self.is_txt.zero_()
-            self.is_txt[:, :t + 1] = (hist >= self.sparse['n_img']).to(torch.uint8)
-            self.len64.fill_(t)
-            self.plan_err.zero_()
+            self.sparse = dict(n_img=int(sparse['n_img']), flags=(hist >= int(sparse['n_img'])).to(torch.uint8))
+        self._reset_run(ids, pos, t)
         # the draw generator of the fused tail: a fresh seed per run from torch's (seedable) host generator
         self.seed_dev.copy_(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64), non_blocking=True)
         graph = self.sample_graphs.get(key)

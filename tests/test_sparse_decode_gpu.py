@@ -108,8 +108,9 @@ def test_attn_decode_gather_matches_softmax_over_the_gathered_keys(b, heads, t, 
     assert err < 2e-2 * ref.abs().max().item(), err
 
 
-def _fill(is_sparse, num_pivot, monkeypatch, pivots="device"):
-    """Greedy filling of 60 image tokens after a 20-token context with a 4 x 4 = 16-key window."""
+def _fill(is_sparse, num_pivot, monkeypatch, pivots="device", text_gen=False):
+    """Greedy filling of 60 tokens after a short context with a 4 x 4 = 16-key window: image tokens after [BOI1], or text
+    tokens (no [BOI1] in the context: generation/sampling.py starts in the text vocabulary) when text_gen."""
     from cogview_b200.generation import sampling
     from cogview_b200.model import GPT2Model
     monkeypatch.setenv("COGVIEW_B200_SPARSE_PIVOTS", pivots)
@@ -130,7 +131,7 @@ def _fill(is_sparse, num_pivot, monkeypatch, pivots="device"):
     tok = sampling.get_tokenizer(A)
     g = torch.Generator().manual_seed(3)
     text = torch.randint(recipes.IMG_VOCAB, recipes.IMG_VOCAB + 100, (10,), generator=g).tolist()
-    seq = [tok['[ROI1]']] + text + [tok['[BASE]'], tok['[BOI1]']] + [-2] * 60
+    seq = [tok['[ROI1]']] + text + ([] if text_gen else [tok['[BASE]'], tok['[BOI1]']]) + [-2] * 60
     with torch.no_grad():
         out = sampling.filling_sequence(m, torch.tensor(seq, dtype=torch.long, device="cuda"), A)
     return out.cpu(), m
@@ -156,3 +157,22 @@ def test_sparse_generation_on_the_device(monkeypatch):
     assert int(gen.max()) < recipes.IMG_VOCAB and few.shape == dense.shape
     n = int(r2.n_keys.item())
     assert n < few.shape[1]                              # a strict subset of the keys was attended at the last step
+
+
+def test_sparse_generation_tracks_text_flags_of_generated_tokens(monkeypatch):
+    """Generated TEXT tokens must be flagged as text for the following steps (all text positions are pivots,
+    mpu/sparse_transformer.py:504-510): with every earlier position a text position the key list is every key, so the run
+    must reproduce the dense greedy tokens although only half of the IMAGE positions would be kept (num_pivot /
+    max_sequence_length = 0.5) — a flag written at the wrong position, or not at all, changes the attended set."""
+    dense, _ = _fill(0, 64, monkeypatch, text_gen=True)
+    sparse, m = _fill(2, 64, monkeypatch, text_gen=True)
+    gen = sparse[:, -60:]
+    assert int(gen.min()) >= recipes.IMG_VOCAB            # text tokens were generated
+    agree = (dense == sparse).float().mean().item()
+    print("sparse text generation vs dense greedy tokens: %.3f equal" % agree)
+    assert agree > 0.97
+    r = m.transformer._kv.runner
+    T = sparse.shape[1]
+    flags = r.is_txt[:, :T - 1].cpu().bool()               # the last sampled token is flagged when it is fed
+    assert torch.equal(flags, sparse[:, :T - 1] >= recipes.IMG_VOCAB)
+    assert int(r.plan_err.item()) == 0
