@@ -778,8 +778,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload_name = ("configs[1]: CogView-base 4B (48L, d=2560, 40H, V=58240), seq 1089, bf16, AR sampling: prefill 65 "
-                     "+ generate %d tokens, %d beams/GPU, top-k 200; persistent one-kernel decode step + fused "
-                     "sampling kernel (CUDA graph)" % (args.gen_tokens, args.batch))
+                     "+ generate %d tokens, %d beams/GPU, top-k 200; weight-streaming decode kernels + one sampling "
+                     "kernel, one CUDA-graph replay per token" % (args.gen_tokens, args.batch))
     # BASELINE.json's metric; `value` is the AR-sampling tokens/s (configs[1]), the training step (configs[2]) and the
     # VQ-VAE round trip (configs[3]) are summarised in config.train / config.vqvae and in full in `train` / `vqvae`
     base = dict(metric="tokens/sec (train + AR sample) CogView-4B seq1089 @1/2/4/8 B200; %roofline", unit="tokens/s",
