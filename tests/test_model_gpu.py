@@ -389,3 +389,36 @@ def test_sparse_inference_with_pivots_matches_the_oracle(data):
             worst = max(worst, (lg.float().cpu() - o_lg).abs().max().item() / scale)
         print("sparse inference with pivots: worst logits error / scale %.3e" % worst)
         assert worst < 2e-2
+
+
+def test_single_token_forward_after_a_sampled_run_returns_its_own_logits(data):
+    """A graph-sampled generate_run followed by an ordinary single-token forward on the same model (same pooled decode
+    runner): the forward must return the logits of ITS step — not the buffer the sampling graph wrote and modified in place
+    (temperature, -inf masks).  Reference behaviour: every call of GPT2Model.forward returns fresh logits
+    (model/gpt2_modeling.py:106-123)."""
+    t0, n = 20, 5
+    ctx, pos = data["tokens"][:, :t0].cuda(), data["pos"][:, :t0].cuda()
+    last = data["tokens"][:, t0:t0 + 1].cuda()
+    mask = torch.tril(torch.ones((1, 1, t0, t0), device="cuda"))
+
+    def pos_at(p):
+        return torch.full((2, 1), p, dtype=torch.long, device="cuda")
+    with torch.no_grad():
+        ma = build(max_memory_length=CFG["max_sequence_length"], mems_mode="kv").eval()
+        _, *mems = ma(ctx, pos, mask, None, None, 0)
+        res = ma.generate_run(last, t0, mems, n, 1.0, 1, [slice(recipes.IMG_VOCAB, None)])
+        assert res is not None
+        new, _, mems = res
+        assert new.shape == (2, n) and mems[0].size(1) == t0 + n
+        lg_a, *_ = ma(new[:, n - 1:n].contiguous(), pos_at(t0 + n), 0, None, None, 0, *mems)
+        # the same token history fed one token at a time through forward only
+        mb = build(max_memory_length=CFG["max_sequence_length"], mems_mode="kv").eval()
+        _, *mems_b = mb(ctx, pos, mask, None, None, 0)
+        fed = torch.cat((last, new[:, :n - 1]), dim=1)
+        for i in range(n):
+            lg_i, *mems_b = mb(fed[:, i:i + 1].contiguous(), pos_at(t0 + i), 0, None, None, 0, *mems_b)
+            # greedy run: the token the run sampled after feeding fed[:, i] is the arg-max over the image vocabulary
+            assert torch.equal(lg_i[:, -1, :recipes.IMG_VOCAB].float().argmax(-1), new[:, i])
+        lg_b, *_ = mb(new[:, n - 1:n].contiguous(), pos_at(t0 + n), 0, None, None, 0, *mems_b)
+    scale = lg_b.abs().max().item()
+    assert (lg_a.float() - lg_b.float()).abs().max().item() < 1e-3 * scale
